@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 SBP hot path (BASELINE.json metric: GDOF/s for batched SBP apply,
+% of HBM peak, 1/2/4/8 GPU).
+
+    python bench.py --gpus N --steps K --warmup W            # native arm (CUDA kernels through the C ABI)
+    python bench.py --impl reference ...                     # reference arm: the reference's CPU path on host cores
+
+Workload at every N (weak scaling): BASELINE config 2 PER GPU -- 1D Legendre (LGL) operator N = 64 applied to a batch
+of 2^20 independent Float64 nodal vectors (`mul!(dU, D, U)`; U = dU = 512 MiB, far larger than the 126 MB L2, and two
+buffer pairs are rotated).  A step is one pass of the hot path over the batch.  DOF = one nodal output value;
+GDOF/s = N*B*ranks / t / 1e9.  Algorithmic traffic 16 B/DOF (read U once, write dU once).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_NODES = 64
+BATCH = 1 << 20
+BYTES_PER_DOF = 16.0
+FLOPS_PER_DOF = 2.0 * N_NODES  # 2 N^2 per instance / N outputs
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak():
+    """FP64 tensor (DMMA) peak measured by tools/microbench on this pool, committed under profiles/."""
+    p = os.path.join(ROOT, "profiles", "microbench_b200.json")
+    try:
+        d = json.load(open(p))
+        return max(max(v.values()) for v in d["dmma_tflops"].values()), d.get("dfma_tflops")
+    except Exception:
+        return None, None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's C port of the reference CPU path, timed on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(sample_instances, steps, warmup, threads):
+    """per-instance dgemv loop (what `mul!(du, D, u)` does for each vector) over `threads` host threads."""
+    from oracle import c_oracle as CO
+    from oracle import sbp_oracle as O
+
+    D = O.PolynomialBasesOperator("LobattoLegendre", -1.0, 1.0, N_NODES).matrix()
+    rng = np.random.default_rng(0)
+    U = rng.uniform(-1, 1, (sample_instances, N_NODES))
+    Y = np.empty_like(U)
+    for _ in range(warmup):
+        CO.apply_dense(D, U, Y=Y, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        CO.apply_dense(D, U, Y=Y, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return sample_instances * N_NODES * steps / dt / 1e9, dt / steps
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import c_oracle as CO
+
+    threads = CO.max_threads()
+    sample = 1 << 18  # bounded sample of the same workload: 2^18 of the 2^20 instances per step
+    gdofs, sec = cpu_reference_rate(sample, args.steps, max(args.warmup, 1), threads)
+    line = {
+        "impl": "reference", "metric": "GDOF/s (batched SBP operator apply, Float64)", "value": gdofs,
+        "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: 1D Legendre (LGL) operator N=64, mul! over a batch of Float64 vectors",
+                   "N": N_NODES, "batch_per_step": sample},
+        "cpu_baseline": {"value": gdofs, "unit": "GDOF/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} of {BATCH} instances per step, per-instance dgemv loop (oracle/oracle_c.c) "
+                                   f"spread over {threads} OpenMP threads; the reference itself is Julia and cannot run "
+                                   "in this image"},
+        "e2e": {"value": gdofs, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------------
+def time_steps(torch, fn, steps):
+    """K steps, CUDA events around every step on the launching stream; returns (total_ms, per-step ms list)."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
+    for i in range(steps):
+        fn(i)
+        evs[i + 1].record()
+    evs[-1].synchronize()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return evs[0].elapsed_time(evs[-1]), per
+
+
+def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
+    """Secondary BASELINE configs (few steps each) so that one bench line also covers the subcell table + energy,
+    the fused 2D advection RHS and the large dense DGEMM."""
+    out = {}
+    dev = torch.device("cuda", ctx.device)
+
+    def bench(fn, dofs, bytes_per_dof, flops=None):
+        for _ in range(3):
+            fn(0)
+        torch.cuda.synchronize()
+        tot, per = time_steps(torch, fn, steps)
+        ms = float(np.median(per))
+        r = {"gdof_s": dofs / ms / 1e6, "ms": ms, "hbm_gbs": dofs * bytes_per_dof / ms / 1e6,
+             "hbm_frac": dofs * bytes_per_dof / ms / 1e6 / hbm_peak}
+        if flops:
+            r["tflops"] = flops / ms / 1e9
+        return r
+
+    try:  # config 4: subcell table N=16, G=8, B=2^22, fused per-instance energy + global sum
+        N, G, B = 16, 8, 1 << 22
+        ops = []
+        for i, NL in enumerate(range(4, 12)):
+            xM = -1.0 + 2.0 * NL / N
+            ops.append(S.couple_subcell(S.legendre_derivative_operator(-1.0, xM, NL),
+                                        S.legendre_derivative_operator(xM, 1.0, N - NL), xM,
+                                        "no" if i % 2 == 0 else "central"))
+        table = S.OperatorTable(ops)
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+        E = torch.empty(B + 1, dtype=torch.float64, device=dev)
+        op = table.device_op(ctx)
+        lib, h = ctx._lib, ctx.handle
+
+        def f4(i):
+            S._lib.check(lib.sbp_apply_table(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, None,
+                                             1.0, 0.0, C.c_void_p(E.data_ptr()), C.c_void_p(E.data_ptr() + 8 * B)))
+
+        out["config4_subcell_table_energy"] = bench(f4, B * N, 16.0 + 8.0 / N)
+        del U, Y, E
+    except Exception as e:  # pragma: no cover
+        out["config4_subcell_table_energy"] = {"error": str(e)[:200]}
+    try:  # config 3: 2D MFSBP advection RHS with SAT, 36x36 jittered cloud, ellipsoid sparsity, B = 65536
+        n1, B = 36, 65536
+        D1 = S.mattsson_nordstrom_2004(2, -1.0, 1.0, n1)
+        D2 = S.tensor_product_operator_2D(D1)
+        rng = np.random.default_rng(0)
+        nodes = D2.grid.copy()
+        dx = 2.0 / (n1 - 1)
+        interior = np.ones(D2.N, bool)
+        interior[np.unique(D2.boundary_indices)] = False
+        nodes[interior] += dx / 6 * (1 - 2 * rng.uniform(size=(int(interior.sum()), 2)))
+        Ds = []
+        for dim, lengths in ((0, (0.14, 0.08)), (1, (0.08, 0.14))):
+            pat = S.neighborhood_sparsity_pattern(nodes, lengths)
+            pat = pat | pat.T | np.eye(D2.N, dtype=bool)
+            Dd = D2.Ds[dim].copy()
+            extra = pat & (Dd == 0)
+            Dd[extra] = 0.05 * rng.normal(size=int(extra.sum()))
+            Ds.append(Dd)
+        Dm = S.MultidimensionalMatrixDerivativeOperator(nodes, D2.boundary_indices, D2.normals, D2.weights(),
+                                                        D2.weights_boundary, Ds, 2, corners=D2.corners)
+        a = (1.0, 1.0)
+        semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(
+            Dm, a, lambda x, t: float(np.exp(-30 * ((x[0] - t) ** 2 + (x[1] - t) ** 2))), storage="sparse")
+        N = Dm.N
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+        u, du = S.DeviceBatch.from_torch(ctx, U), S.DeviceBatch.from_torch(ctx, Y)
+        nnz = int(np.count_nonzero(semi.cache["A"]))
+        r = bench(lambda i: semi(du, u, None, 0.1), B * N, 16.0, flops=2.0 * nnz * B)
+        r["N"], r["nnz_per_row"] = N, nnz / N
+        out["config3_advection2d_rhs_sat"] = r
+        del U, Y
+    except Exception as e:  # pragma: no cover
+        out["config3_advection2d_rhs_sat"] = {"error": str(e)[:200]}
+    try:  # config 5 (reduced batch): dense N = 4096 operator, B = 8192 -> DMMA DGEMM
+        N, B = 4096, 8192
+        rng = np.random.default_rng(0)
+        Sk = rng.normal(size=(N, N))
+        Sk = Sk - Sk.T
+        w = rng.uniform(0.5, 1.5, N)
+        w *= 4.0 / w.sum()
+        Dmat = Sk / w[:, None]
+        op = S.upload_dense(ctx, Dmat, w)
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+        lib, h = ctx._lib, ctx.handle
+
+        def f5(i):
+            S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
+
+        r = bench(f5, B * N, 16.0 + 8.0 * N / B, flops=2.0 * N * N * B)
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        Dt = torch.from_numpy(np.ascontiguousarray(Dmat)).to(dev)
+        for _ in range(2):
+            torch.matmul(U, Dt.T, out=Y)
+        t0.record()
+        for _ in range(3):
+            torch.matmul(U, Dt.T, out=Y)
+        t1.record()
+        t1.synchronize()
+        r["cublas_dgemm_tflops"] = 2.0 * N * N * B * 3 / t0.elapsed_time(t1) / 1e9
+        out["config5_dense4096_dgemm_B8192"] = r
+        del U, Y, Dt
+    except Exception as e:  # pragma: no cover
+        out["config5_dense4096_dgemm_B8192"] = {"error": str(e)[:200]}
+    return out
+
+
+def run_native(args):
+    import torch
+
+    import sbp_b200 as S
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the native arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = S.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    lib, h = ctx._lib, ctx.handle
+
+    N, B = N_NODES, BATCH  # per GPU (weak scaling)
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, N)
+    op = D.device_op(ctx)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    bufs = []
+    for _ in range(2):  # two (U, dU) pairs rotated: 2 GiB of traffic between reuses of a line
+        U = torch.rand((B, N), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        bufs.append((U, torch.empty_like(U)))
+
+    def step(i):
+        U, Y = bufs[i & 1]
+        S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    total_ms, per = time_steps(torch, step, args.steps)
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    barrier()
+    total_ms = float(t.item())
+
+    # the path's only collective: a sum of scalars (global discrete energy); done once, outside the timed steps
+    E = torch.zeros(2, dtype=torch.float64, device=dev)
+    S._lib.check(lib.sbp_integrate(h, op.handle, C.c_void_p(bufs[0][0].data_ptr()), None, B, 1, None,
+                                   C.c_void_p(E.data_ptr())))
+    if dist is not None:
+        dist.all_reduce(E)
+    global_energy = float(E[0].item())
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    e2e_steps = max(2, min(args.steps, 5))
+    hU, hY = ctx.pinned_empty((B, N)), ctx.pinned_empty((B, N))
+    hU[:] = np.random.default_rng(rank).uniform(-1, 1, (B, N))
+
+    def e2e_step():
+        S._lib.check(lib.sbp_apply_host(h, op.handle, hY.ctypes.data_as(C.c_void_p), hU.ctypes.data_as(C.c_void_p), B,
+                                        1.0, 0.0, 0))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    checksum = float(hY[:: max(1, B // 1024)].sum())
+    ctx.free_pinned(hU), ctx.free_pinned(hY)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = measured_peaks()
+    dofs_step = float(N) * B
+    kernel_ms = float(np.mean(per))
+    achieved = dofs_step * BYTES_PER_DOF / kernel_ms / 1e6  # GB/s
+    fp64_dmma, fp64_dfma = fp64_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("config2_dense_small_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "GDOF/s (batched SBP operator apply, Float64)",
+        "value": world * dofs_step * args.steps / total_ms / 1e6,
+        "unit": "GDOF/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config2: 1D Legendre (LGL) operator N=64, mul!(dU, D, U) over 2^20 Float64 vectors per GPU",
+                   "N": N, "batch_per_gpu": B, "bytes_per_dof": BYTES_PER_DOF,
+                   "l2": "inputs (512 MiB) and outputs (512 MiB) exceed the 126 MB L2; two buffer pairs rotated",
+                   "parallelism": f"batch sharded over {world} GPU(s), operator replicated, no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "k_dense_small<NT=8> (DMMA.8x8x4)",
+                     "kernel_ms": kernel_ms,
+                     "fp64_tflops": dofs_step * FLOPS_PER_DOF / kernel_ms / 1e9,
+                     "fp64_dmma_peak_tflops": fp64_dmma,
+                     "note": "N=64 has AI = 8 flop/B: time >= max(bytes/HBM, flops/FP64 peak); both fractions reported"},
+        "e2e": {"value": world * dofs_step * e2e_steps / e2e_s / 1e9, "unit": "GDOF/s",
+                "h2d_bytes_per_step": int(dofs_step * 8), "d2h_bytes_per_step": int(dofs_step * 8),
+                "steps": e2e_steps, "api": "sbp_apply_host (pinned host buffers, chunked H2D/compute/D2H overlap)",
+                "checksum": checksum},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "global_energy_allreduce": global_energy,
+    }
+    if fp64_dmma:
+        line["roofline"]["fp64_frac"] = line["roofline"]["fp64_tflops"] / fp64_dmma
+    if world == 1:
+        from oracle import c_oracle as CO
+
+        threads = CO.max_threads()
+        g1, s1 = cpu_reference_rate(1 << 14, 2, 1, 1)
+        sample = 1 << 18
+        steps_cpu = max(2, int(4.0 / max(s1 * (sample / (1 << 14)) / threads, 1e-3)))
+        gall, _ = cpu_reference_rate(sample, min(steps_cpu, 50), 1, threads)
+        line["cpu_baseline"] = {"value": gall, "unit": "GDOF/s", "cores": threads, "kind": "port",
+                                "single_core_value": g1,
+                                "sample": f"{sample} of {B} instances per pass, per-instance dgemv loop (oracle/oracle_c.c) "
+                                          f"on {threads} OpenMP threads; single-thread rate in single_core_value"}
+        if not args.no_extra:
+            line["extra"] = extra_workloads(torch, S, ctx, hbm_peak)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3/4/5)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

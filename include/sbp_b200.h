@@ -1,0 +1,207 @@
+/* sbp_b200.h -- C ABI of libsbp_b200.so (CUDA sm_100a).
+ *
+ * Drop-in boundary for the data-parallel hot path of SummationByPartsOperatorsExtra.jl:
+ * batched application of assembled SBP derivative operators, the fused linear-advection RHS
+ * with SAT boundary terms, and the P-weighted reductions (mass / energy / analysis quantities).
+ * The reference has no FFI layer (pure Julia multiple dispatch); each entry point below names the
+ * reference method it replaces (paths relative to the reference repository root).  The Julia shim
+ * that binds these with `ccall` is shown in INTEGRATION.md and shipped as
+ * summationbypartsoperatorsextra.jl_b200/julia/SBPB200.jl.
+ *
+ * Conventions
+ *  - every function returns an int32 status: 0 = SBP_OK, < 0 = error; the message of the last
+ *    error on the calling thread is returned by sbp_last_error().
+ *  - "batch" layout: a batch of B nodal vectors of N nodes is ONE array of B*N doubles with each
+ *    instance contiguous (Julia `Matrix{Float64}(N, B)`, column-major; numpy (B, N) C-order).
+ *    Instance b lives at U + b*N.
+ *  - pointers named U, dU, V, g, out, ... are DEVICE pointers (from sbp_malloc or any CUDA
+ *    allocation) unless the name starts with h_.  Host arrays passed to *_create are copied;
+ *    they are borrowed only for the duration of the call.
+ *  - one sbp_ctx per device and host thread; calls on a ctx are stream-ordered and asynchronous;
+ *    sbp_ctx_sync / sbp_memcpy_d2h synchronise.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    SBP_ECUDA.
+ */
+#ifndef SBP_B200_H
+#define SBP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBP_OK 0
+#define SBP_EINVAL -1   /* bad argument (maps to Julia ArgumentError)                       */
+#define SBP_EDIM -2     /* size mismatch (maps to DimensionMismatch / @argcheck ArgumentError,
+                           src/polynomialbases_operators.jl:143-146, src/subcell_operators.jl:195) */
+#define SBP_ECUDA -3    /* CUDA runtime / launch failure, or no device                      */
+#define SBP_ENOMEM -4   /* device or host allocation failed                                 */
+#define SBP_ENCCL -5    /* NCCL unavailable or failed                                       */
+#define SBP_EUNSUPPORTED -6
+
+typedef struct sbp_ctx sbp_ctx; /* device + stream + scratch                                  */
+typedef struct sbp_op sbp_op;   /* immutable device-resident operator                         */
+
+/* operator kinds (sbp_op_info) */
+#define SBP_OP_DENSE 1
+#define SBP_OP_SPARSE 2
+#define SBP_OP_TABLE 3
+#define SBP_OP_ADVECTION2D 4
+#define SBP_OP_ADVECTION1D 5
+
+/* flags for sbp_op_dense_create */
+#define SBP_DENSE_AUTO 0        /* pick kernel from N (smem-resident DMMA tiles or tiled DGEMM)  */
+#define SBP_DENSE_FORCE_GEMM 1  /* always use the tiled DGEMM path                                */
+#define SBP_DENSE_NO_SYMMETRY 2 /* do not exploit centro-(anti)symmetry even if D has it exactly  */
+
+/* ---- library / context ----------------------------------------------------------------- */
+int32_t sbp_version(void);
+const char* sbp_last_error(void);
+int32_t sbp_device_count(int32_t* n);
+int32_t sbp_ctx_create(int32_t device, sbp_ctx** ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx's own. */
+int32_t sbp_ctx_set_stream(sbp_ctx* ctx, void* cuda_stream);
+int32_t sbp_ctx_get_stream(sbp_ctx* ctx, void** cuda_stream);
+int32_t sbp_ctx_sync(sbp_ctx* ctx);
+int32_t sbp_ctx_destroy(sbp_ctx* ctx);
+/* sm count, L2 bytes, max dynamic smem per block, total global memory */
+int32_t sbp_ctx_device_info(sbp_ctx* ctx, int32_t* sm_count, int64_t* l2_bytes, int64_t* smem_optin,
+                            int64_t* global_bytes);
+/* number of kernels this ctx has launched since creation (for harness accounting) */
+int64_t sbp_ctx_launch_count(sbp_ctx* ctx);
+
+/* ---- memory ---------------------------------------------------------------------------- */
+int32_t sbp_malloc(sbp_ctx* ctx, size_t bytes, void** dptr);
+int32_t sbp_free(sbp_ctx* ctx, void* dptr);
+int32_t sbp_host_alloc(size_t bytes, void** hptr); /* pinned host memory */
+int32_t sbp_host_free(void* hptr);
+int32_t sbp_memcpy_h2d(sbp_ctx* ctx, void* dptr, const void* h_src, size_t bytes); /* async on ctx stream */
+int32_t sbp_memcpy_d2h(sbp_ctx* ctx, void* h_dst, const void* dptr, size_t bytes); /* synchronises */
+int32_t sbp_memset(sbp_ctx* ctx, void* dptr, int32_t byte, size_t bytes);
+
+/* ---- operators (uploaded once; construction stays on the CPU) ----------------------------- */
+
+/* Dense N x N operator, `h_D` column-major with leading dimension ldd (Julia Matrix), optional
+ * quadrature weights h_w (N, may be NULL -> no integrate/energy support) and a constant `scale`
+ * folded into every apply (the `jac` of src/polynomialbases_operators.jl:148).
+ * Replaces the storage side of PolynomialBasesDerivativeOperator (src/polynomialbases_operators.jl:7-31),
+ * upstream MatrixDerivativeOperator (built at ext/function_space_operators.jl:13-14) and one
+ * direction D[dim] of MultidimensionalMatrixDerivativeOperator
+ * (ext/multidimensional_function_space_operators.jl:20-22). */
+int32_t sbp_op_dense_create(sbp_ctx* ctx, int32_t N, const double* h_D, int32_t ldd, const double* h_w,
+                            double scale, int32_t flags, sbp_op** op);
+
+/* CSR operator (0-based, int32).  For operators whose dense storage in the reference is
+ * structurally sparse (banded FSBP, ellipsoid-neighbourhood MFSBP: src/utils/sparsity_patterns.jl:48-60). */
+int32_t sbp_op_sparse_create(sbp_ctx* ctx, int32_t N, const int32_t* h_rowptr, const int32_t* h_col,
+                             const double* h_val, const double* h_w, double scale, sbp_op** op);
+/* Same, extracting the exact non-zeros of a dense column-major matrix. */
+int32_t sbp_op_sparse_from_dense(sbp_ctx* ctx, int32_t N, const double* h_D, int32_t ldd, const double* h_w,
+                                 double scale, sbp_op** op);
+
+/* Table of G dense N x N operators with per-operator weights (h_D: G matrices, each column-major
+ * N x N; h_w: G*N).  Serves SubcellOperator families with varying split point: the caller passes
+ * D_g = inv(Diagonal(w_L (+) w_R)) * (Q_left + Q_right) (src/subcell_operators.jl:183-186), which the
+ * reference rebuilds on every mul! (src/subcell_operators.jl:272). */
+int32_t sbp_op_table_create(sbp_ctx* ctx, int32_t N, int32_t G, const double* h_D, const double* h_w,
+                            sbp_op** op);
+
+/* 2D linear advection bundle (MultidimensionalLinearAdvectionNonperiodicSemidiscretization,
+ * src/conservation_laws/multidimensional_linear_advection.jl:22-41).  `A` = a1*Dx + a2*Dy as a dense or
+ * sparse op (kept referenced; destroy it after the bundle), h_b = diagonal of B = inv(P)*(a1*B_x+a2*B_y)
+ * (N), h_w = diagonal of P (N), h_mode (N): 0 interior, 1 inflow, 2 outflow -- the state left by the
+ * sequential set_bc! loop (:60-71, last writer wins at corners).  Boundary entry lists (length Nb, with
+ * duplicated corner nodes) feed energy_rate_boundary (:98-105): h_bnd_node (0-based node of entry i) and
+ * h_bnd_tau[i] = weights_boundary[i] * dot(normals[i], a). */
+int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h_b, const double* h_w,
+                                  const int32_t* h_mode, int32_t Nb, const int32_t* h_bnd_node,
+                                  const double* h_bnd_tau, sbp_op** op);
+
+/* 1D variable-coefficient advection bundle (upstream VariableLinearAdvectionNonperiodicSemidiscretization,
+ * used at examples/RBF_FSBP_advection.jl:37-38): du = -D*(a.*u) + SATs at first/last node.
+ * `D` dense or sparse op with weights; h_a (N) nodal speeds. */
+int32_t sbp_op_advection1d_create(sbp_ctx* ctx, const sbp_op* D, const double* h_a, sbp_op** op);
+
+int32_t sbp_op_destroy(sbp_op* op);
+/* kind, N, table size G (1 otherwise), nnz (N*N for dense), kernel variant chosen (SBP_KERNEL_*) */
+int32_t sbp_op_info(const sbp_op* op, int32_t* kind, int32_t* N, int32_t* G, int64_t* nnz, int32_t* variant);
+
+#define SBP_KERNEL_DMMA_SMEM 1     /* operator fragments resident in shared memory, DMMA tiles         */
+#define SBP_KERNEL_DMMA_SMEM_SYM 2 /* same, even/odd split of a centro-antisymmetric operator          */
+#define SBP_KERNEL_DGEMM_TILED 3   /* large N: tiled DMMA DGEMM, operator streamed through L2          */
+#define SBP_KERNEL_CSR_SMEM 4      /* sparse: instance tile staged in smem, CSR rows per thread        */
+#define SBP_KERNEL_TABLE 5
+
+/* ---- hot path --------------------------------------------------------------------------- */
+
+/* dU[:,b] = alpha * scale * D * U[:,b] + beta * dU[:,b]   for b in [0,B).
+ * Replaces LinearAlgebra.mul!(dest, D, u, alpha, beta) of src/polynomialbases_operators.jl:139-149,
+ * src/subcell_operators.jl:270-280 and the upstream MatrixDerivativeOperator / D[dim] methods, applied to
+ * every instance of the batch.  N is implied by the operator; U and dU hold B*N doubles; they must not
+ * alias.  With beta == 0 dU is write-only (NaNs in dU are not propagated, as in BLAS). */
+int32_t sbp_apply(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                  double beta);
+
+/* Operator-table apply: instance b uses operator op_index[b] (device int32 array, length B), or, when
+ * op_index == NULL, operator (b % G).  Optionally fuses the discrete energy integrate(abs2, u, D_g) =
+ * sum_i w_g[i] u_i^2 (src/subcell_operators.jl:92-94) per instance (energy, B doubles or NULL) and its
+ * sum over the batch (energy_sum, one device double or NULL; overwritten). Also valid for DENSE ops (G=1). */
+int32_t sbp_apply_table(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                        const int32_t* op_index, double alpha, double beta, double* energy,
+                        double* energy_sum);
+
+/* out[b] = sum_i w_i * f(U[i,b], V[i,b]) with mode 0: u, 1: u^2 (abs2), 2: u*v ; out_sum (device, may be
+ * NULL) receives the sum over the batch.  Replaces integrate(func, u, D)
+ * (src/polynomialbases_operators.jl:66-68, src/subcell_operators.jl:92-94) and the P-weighted sums of
+ * analyze_quantities.  V may be NULL for modes 0/1. */
+int32_t sbp_integrate(sbp_ctx* ctx, const sbp_op* op, const double* U, const double* V, int64_t B,
+                      int32_t mode, double* out, double* out_sum);
+
+/* U[i,b] <- factor * U[i,b] * w_i  (inverse == 0)   or   factor * U[i,b] / w_i  (inverse != 0).
+ * Replaces scale_by_mass_matrix! / scale_by_inverse_mass_matrix!
+ * (src/polynomialbases_operators.jl:82-114, src/subcell_operators.jl:190-220). */
+int32_t sbp_scale_by_mass_matrix(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, double factor,
+                                 int32_t inverse);
+
+/* Fused 2D advection RHS (functor at src/conservation_laws/multidimensional_linear_advection.jl:73-81 with
+ * set_bc! :60-71 folded in):  dU[j,b] = -sum_k A[j,k] U[k,b] + (mode[j]==inflow ? b_j*(U[j,b]-g_j) : 0).
+ * g holds the boundary data bc(x_j, t) per NODE (N doubles; only inflow entries are read), shared by the
+ * batch when g_stride == 0 or per instance at g + b*g_stride.  quantities (device, 7*B doubles or NULL)
+ * receives analyze_quantities (:83-108) per instance in the reference's order
+ * [mass, mass_rate, mass_rate_boundary, energy, energy_rate, energy_rate_boundary,
+ *  energy_rate_boundary_dissipation]. */
+int32_t sbp_rhs_advection2d(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                            const double* g, int64_t g_stride, double* quantities);
+
+/* Fused 1D advection RHS with Godunov SATs (upstream semidiscretization; §3.3 of SURVEY.md):
+ * dU = -D*(a.*U); dU[0] += (fl - a0 U0)/w0; dU[N-1] -= (fr - aN UN)/wN with fl = godunov(bc_left, U0, a0),
+ * fr = godunov(UN, bc_right, aN).  bc (device): 2 doubles [left,right] shared (bc_stride == 0) or per
+ * instance at bc + b*bc_stride.  quantities as above (src/conservation_laws/analysis_callback.jl:136-173). */
+int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                            const double* bc, int64_t bc_stride, double* quantities);
+
+/* Y = a*X + b*Y + c*Z elementwise over n doubles (Z may be NULL): stage updates of the explicit
+ * Runge-Kutta schemes the examples use (SSPRK53, RDPK3SpFSAL49) so that a step never leaves the device. */
+int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a,
+                     double b, double c);
+
+/* ---- multi-GPU: one process per GPU; the only collective is a sum of a few scalars ------------- */
+#define SBP_NCCL_ID_BYTES 128
+int32_t sbp_comm_unique_id(char id[SBP_NCCL_ID_BYTES]);       /* rank 0, then broadcast by the host runtime */
+int32_t sbp_comm_init(sbp_ctx* ctx, int32_t nranks, int32_t rank, const char id[SBP_NCCL_ID_BYTES]);
+int32_t sbp_allreduce_sum(sbp_ctx* ctx, double* dptr, int32_t count); /* ncclAllReduce(double, sum), in place */
+int32_t sbp_comm_destroy(sbp_ctx* ctx);
+
+/* ---- host-buffer convenience (end-to-end path: pinned staging + chunked H2D/compute/D2H overlap) */
+/* h_dU = alpha*scale*D*h_U + beta*h_dU for host arrays; copies are pipelined in chunks of
+ * `chunk_instances` (0 = auto) over three streams.  This is what `mul!(dU::Matrix, D, U::Matrix)` on
+ * host arrays maps to. */
+int32_t sbp_apply_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B,
+                       double alpha, double beta, int64_t chunk_instances);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBP_B200_H */

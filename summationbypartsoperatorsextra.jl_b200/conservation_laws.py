@@ -1,0 +1,284 @@
+"""Host-side mirror of src/conservation_laws/ (semidiscretizations + analysis callback) on device batches.
+
+    semi = MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, bc)
+    semi(du, u, p, t)                           # in-place RHS for every instance of the batch
+    analyze_quantities(semi, du, u, p, t)       # (B, 7) host array in the reference's order
+    cb = AnalysisCallback(semi; dt=0.01) / interval=...;  tstops(cb), quantities(cb)
+    semidiscretize(u0func, semi, tspan)
+
+The constructors do the reference's one-time host assembly (multidimensional_linear_advection.jl:22-41:
+A = a1*Dx + a2*Dy, B = inv(P)*(a1*B_x + a2*B_y)) and resolve the sequential `set_bc!` loop (:60-71) into a
+per-node mode (0 interior / 1 inflow / 2 outflow; later boundary entries overwrite earlier ones, i.e. corners
+keep the LAST entry).  Each RHS call is ONE fused device pass (operator apply + SAT); `bc(x, t)` is a host
+callable, evaluated at the inflow nodes only, once per distinct t, and uploaded as N doubles.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, DimensionMismatch, check
+from .device import Context, DeviceBatch, RawBuffer
+from .operators import (DerivativeOperator, MultidimensionalMatrixDerivativeOperator, _DeviceOp, _as_f64, _ptr,
+                        upload_dense, upload_sparse)
+
+
+class AbstractSemidiscretization:
+    pass
+
+
+class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemidiscretization):
+    """u_t + a . grad u = 0 with boundary data bc(x, t)
+    (src/conservation_laws/multidimensional_linear_advection.jl:10-42)."""
+
+    def __init__(self, derivative: MultidimensionalMatrixDerivativeOperator, a, bc, storage: str | None = None):
+        if len(a) != 2 or len(derivative.Ds) != 2:
+            raise ArgumentError("Only 2D is supported")  # "Only support 2D for now" (:30)
+        D = derivative
+        self.derivative, self.a, self.bc = D, (float(a[0]), float(a[1])), bc
+        self.storage = storage or D.storage
+        A = self.a[0] * D.Ds[0] + self.a[1] * D.Ds[1]  # :33
+        invP = 1.0 / D.weights()  # :34
+        B_x = D.mass_matrix_boundary_diag(0)  # :35
+        B_y = D.mass_matrix_boundary_diag(1)  # :36
+        B = invP * (self.a[0] * B_x + self.a[1] * B_y)  # :37
+        mode = np.zeros(D.N, dtype=np.int32)
+        an = D.normals @ np.asarray(self.a)
+        for i, j in enumerate(D.boundary_indices):  # set_bc! loop order (:62-70)
+            mode[j] = 1 if an[i] < 0 else 2
+        self.cache = {"A": A, "B": B, "tmp1": None}
+        self.mode = mode
+        self.inflow_nodes = np.flatnonzero(mode == 1)
+        self.bnd_tau = D.weights_boundary * an  # tau_i of analyze_quantities (:101-103)
+        self._dev: dict[int, tuple] = {}
+        self._g_cache: dict[int, tuple] = {}
+
+    # -- device bundle ----------------------------------------------------------------------------------
+    def _want_sparse(self, A):
+        if self.storage == "dense":
+            return False
+        if self.storage == "sparse":
+            return True
+        return A.shape[0] > 128 and np.count_nonzero(A) < 0.15 * A.size
+
+    def device_op(self, ctx: Context) -> _DeviceOp:
+        ent = self._dev.get(id(ctx))
+        if ent is None:
+            D = self.derivative
+            A = self.cache["A"]
+            inner = upload_sparse(ctx, A, D.weights()) if self._want_sparse(A) else upload_dense(ctx, A, D.weights())
+            b, w = _as_f64(self.cache["B"]), _as_f64(D.weights())
+            node = np.ascontiguousarray(D.boundary_indices, dtype=np.int32)
+            tau = _as_f64(self.bnd_tau)
+            h = C.c_void_p()
+            check(ctx._lib.sbp_op_advection2d_create(ctx.handle, inner.handle, b.ctypes.data_as(C.c_void_p),
+                                                     w.ctypes.data_as(C.c_void_p),
+                                                     self.mode.ctypes.data_as(C.c_void_p), len(node),
+                                                     node.ctypes.data_as(C.c_void_p), tau.ctypes.data_as(C.c_void_p),
+                                                     C.byref(h)))
+            ent = (_DeviceOp(ctx, h), inner)
+            self._dev[id(ctx)] = ent
+        return ent[0]
+
+    def boundary_values(self, t: float) -> np.ndarray:
+        """g_j = bc(x_j, t) at inflow nodes (0 elsewhere) -- the data `set_bc!` writes into tmp1 (:65-66)."""
+        g = np.zeros(self.derivative.N)
+        nodes = self.derivative.grid
+        for j in self.inflow_nodes:
+            g[j] = self.bc(nodes[j], t)
+        return g
+
+    def _device_g(self, ctx: Context, t: float):
+        ent = self._g_cache.get(id(ctx))
+        if ent is None or ent[0] != t:
+            if ent is not None:
+                ent[1].free()
+            ent = (t, ctx.upload_array(self.boundary_values(t)))
+            self._g_cache[id(ctx)] = ent
+        return ent[1]
+
+    def __call__(self, du: DeviceBatch, u: DeviceBatch, p=None, t: float = 0.0, g: DeviceBatch | None = None,
+                 quantities: RawBuffer | None = None):
+        """RHS functor (:73-81).  `g` optionally supplies per-instance boundary data as a (B, N) device batch
+        (only inflow entries are read); by default bc(x, t) is evaluated on the host and shared by the batch."""
+        N = self.derivative.N
+        if u.N != N or du.N != N or du.B != u.B:
+            raise DimensionMismatch("du, u and the operator differ in size")
+        ctx = u.ctx
+        op = self.device_op(ctx)
+        if g is None:
+            gptr, gstride = self._device_g(ctx, float(t)).ptr, 0
+        else:
+            if g.shape != u.shape:
+                raise DimensionMismatch("per-instance boundary data must have the shape of u")
+            gptr, gstride = g.ptr, N
+        check(ctx._lib.sbp_rhs_advection2d(ctx.handle, op.handle, _ptr(du.ptr), _ptr(u.ptr), u.B, _ptr(gptr),
+                                           gstride, _ptr(quantities.ptr) if quantities is not None else None))
+        return None
+
+    def __repr__(self):
+        return ("Semidiscretization of the linear advection equation\n"
+                "  $ \\partial_t u(x, t) + a\\cdot \\nabla u(x, t) = 0 $\nwith nonperiodic boundaries")
+
+
+class VariableLinearAdvectionNonperiodicSemidiscretization(AbstractSemidiscretization):
+    """Upstream 1D semidiscretization used by examples/RBF_FSBP_advection.jl:37-38:
+    `VariableLinearAdvectionNonperiodicSemidiscretization(D, nothing, afunc, Val(false), left_bc, right_bc)`;
+    du = -D*(a.*u) with Godunov SATs at both ends."""
+
+    def __init__(self, derivative: DerivativeOperator, dissipation, afunc, split_form, left_bc, right_bc):
+        if dissipation is not None:
+            raise ArgumentError("artificial dissipation is not supported on the device path")
+        if split_form not in (False, None):
+            raise ArgumentError("only the non-split form (Val(false)) is supported")
+        self.derivative = derivative
+        self.a = np.array([afunc(x) for x in derivative.grid], dtype=np.float64)
+        self.left_bc, self.right_bc = left_bc, right_bc
+        self._dev: dict[int, tuple] = {}
+        self._bc_cache: dict[int, tuple] = {}
+
+    def device_op(self, ctx: Context) -> _DeviceOp:
+        ent = self._dev.get(id(ctx))
+        if ent is None:
+            inner = self.derivative.device_op(ctx)
+            a = _as_f64(self.a)
+            h = C.c_void_p()
+            check(ctx._lib.sbp_op_advection1d_create(ctx.handle, inner.handle, a.ctypes.data_as(C.c_void_p),
+                                                     C.byref(h)))
+            ent = (_DeviceOp(ctx, h), inner)
+            self._dev[id(ctx)] = ent
+        return ent[0]
+
+    def _device_bc(self, ctx, t):
+        ent = self._bc_cache.get(id(ctx))
+        if ent is None or ent[0] != t:
+            if ent is not None:
+                ent[1].free()
+            ent = (t, ctx.upload_array(np.array([self.left_bc(t), self.right_bc(t)], dtype=np.float64)))
+            self._bc_cache[id(ctx)] = ent
+        return ent[1]
+
+    def __call__(self, du: DeviceBatch, u: DeviceBatch, p=None, t: float = 0.0, bc: DeviceBatch | None = None,
+                 quantities: RawBuffer | None = None):
+        N = self.derivative.N
+        if u.N != N or du.N != N or du.B != u.B:
+            raise DimensionMismatch("du, u and the operator differ in size")
+        ctx = u.ctx
+        op = self.device_op(ctx)
+        if bc is None:
+            bptr, bstride = self._device_bc(ctx, float(t)).ptr, 0
+        else:
+            if bc.shape != (u.B, 2):
+                raise DimensionMismatch("per-instance boundary data must be (B, 2)")
+            bptr, bstride = bc.ptr, 2
+        check(ctx._lib.sbp_rhs_advection1d(ctx.handle, op.handle, _ptr(du.ptr), _ptr(u.ptr), u.B, _ptr(bptr), bstride,
+                                           _ptr(quantities.ptr) if quantities is not None else None))
+        return None
+
+
+def analyze_quantities(semi, du: DeviceBatch, u: DeviceBatch, p=None, t: float = 0.0, **kw) -> np.ndarray:
+    """`analyze_quantities(semi, du, u, p, t)` (multidimensional_linear_advection.jl:83-108,
+    analysis_callback.jl:136-173): re-evaluates the RHS into `du` (as the callback does, analysis_callback.jl:123)
+    and returns the 7 quantities per instance, shape (B, 7) ((7,) for B == 1)."""
+    if not isinstance(semi, (MultidimensionalLinearAdvectionNonperiodicSemidiscretization,
+                             VariableLinearAdvectionNonperiodicSemidiscretization)):
+        return np.zeros(0)  # fallback method (analysis_callback.jl:134)
+    q = RawBuffer(u.ctx, max(u.B, 1) * 7 * 8)
+    semi(du, u, p, t, quantities=q, **kw)
+    out = q.to_host(np.float64, u.B * 7).reshape(u.B, 7)
+    q.free()
+    return out[0] if u.B == 1 else out
+
+
+class ODEProblem:
+    def __init__(self, f, u0, tspan, p=None):
+        self.f, self.u0, self.tspan, self.p = f, u0, tspan, p
+
+
+def semidiscretize(u0func, semi, tspan, ctx: Context | None = None, batch: int = 1) -> ODEProblem:
+    """`semidiscretize(u0func, semi, tspan)` = ODEProblem{true}(semi, u0func.(grid), tspan); the initial state is
+    uploaded as a batch of `batch` identical instances when a context is given (host array otherwise)."""
+    nodes = semi.derivative.grid
+    u0 = np.array([u0func(x) for x in nodes], dtype=np.float64)
+    if ctx is not None:
+        u0 = ctx.upload(np.tile(u0, (batch, 1)))
+    return ODEProblem(semi, u0, tspan)
+
+
+class AnalysisCallback:
+    """src/conservation_laws/analysis_callback.jl:20-113: records `analyze_quantities` every `interval` accepted
+    steps or every `dt` of simulated time.  Works with `solve_ssprk53` below."""
+
+    def __init__(self, semi, interval: int = 0, dt: float | None = None):
+        if interval > 0 and dt is not None:
+            raise ArgumentError("Setting both `interval` and `dt` is not supported.")  # :78-80
+        self.semi, self.interval, self.dt = semi, int(interval), dt
+        self._tstops: list[float] = []
+        self._quantities: list[np.ndarray] = []
+        self._next_t = None
+
+    def __call__(self, du, u, p, t):
+        self._tstops.append(float(t))
+        self._quantities.append(analyze_quantities(self.semi, du, u, p, t))
+
+    def should_fire(self, step: int, t: float, final: bool) -> bool:
+        if self.dt is not None:
+            if self._next_t is None:
+                self._next_t = t  # initial_affect = true
+            if t >= self._next_t - 1e-12 or final:
+                while self._next_t <= t + 1e-12:
+                    self._next_t += self.dt
+                return True
+            return False
+        return self.interval > 0 and (step % self.interval == 0 or final)
+
+    def __repr__(self):
+        return f"AnalysisCallback(interval={self.interval}, dt={self.dt})"
+
+
+def tstops(cb: AnalysisCallback):
+    return cb._tstops
+
+
+def quantities(cb: AnalysisCallback):
+    return cb._quantities
+
+
+_SSPRK53 = dict(
+    a30=0.355909775063327, a32=0.644090224936674, a40=0.367933791638137, a43=0.632066208361863,
+    a52=0.237593836598569, a54=0.762406163401431, b10=0.377268915331368, b21=0.377268915331368,
+    b32=0.242995220537396, b43=0.238458932846290, b54=0.287632146308408,
+    c1=0.377268915331368, c2=0.754537830662736, c3=0.728985661612188, c4=0.699226135931670)
+
+
+def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None = None) -> DeviceBatch:
+    """Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive=false)`, examples/RBF_FSBP_advection.jl:45-51) with
+    every stage update on the device (sbp_axpbypcz); returns the final state."""
+    k = _SSPRK53
+    u: DeviceBatch = prob.u0
+    semi, p = prob.f, prob.p
+    t, tend = float(prob.tspan[0]), float(prob.tspan[1])
+    du, u1, u2, u3 = u.similar(), u.similar(), u.similar(), u.similar()
+    u = u.copy()
+    step = 0
+    if callback is not None and callback.should_fire(step, t, False):
+        callback(du, u, p, t)
+    while t < tend - 1e-14:
+        h = min(dt, tend - t)
+        semi(du, u, p, t)
+        u1.axpby_(1.0, u, 0.0).axpby_(k["b10"] * h, du)                       # u1 = u + b10 h f(u)
+        semi(du, u1, p, t + k["c1"] * h)
+        u2.axpby_(1.0, u1, 0.0).axpby_(k["b21"] * h, du)                      # u2 = u1 + b21 h f(u1)
+        semi(du, u2, p, t + k["c2"] * h)
+        u3.axpby_(k["a30"], u, 0.0, k["a32"], u2).axpby_(k["b32"] * h, du)    # u3 = a30 u + a32 u2 + b32 h f(u2)
+        semi(du, u3, p, t + k["c3"] * h)
+        u1.axpby_(k["a40"], u, 0.0, k["a43"], u3).axpby_(k["b43"] * h, du)    # u4 (in u1)
+        semi(du, u1, p, t + k["c4"] * h)
+        u.axpby_(k["a52"], u2, 0.0, k["a54"], u1).axpby_(k["b54"] * h, du)    # u5
+        t += h
+        step += 1
+        if callback is not None and callback.should_fire(step, t, t >= tend - 1e-14):
+            callback(du, u, p, t)
+    return u

@@ -1,0 +1,787 @@
+// api.cu -- extern "C" entry points of libsbp_b200.so (see include/sbp_b200.h for the contract and the
+// reference file:line each entry point replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace sbp {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+int32_t ensure_scratch(sbp_ctx* ctx, size_t doubles) {
+    if (ctx->scratch_doubles >= doubles) return SBP_OK;
+    // grown rarely; synchronise so no in-flight kernel still uses the old buffer
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_doubles = 0;
+    size_t n = std::max<size_t>(doubles, 4096);
+    SBP_CUDA(cudaMalloc(&ctx->scratch, n * sizeof(double)));
+    ctx->scratch_doubles = n;
+    return SBP_OK;
+}
+
+int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                              double beta, double* energy, double* energy_sum, const double* cfrag);
+int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                         double beta, const sbp_op* adv, const double* g, int64_t g_stride, const double* colscale);
+int32_t launch_adv1d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B,
+                              const double* bc, int64_t bc_stride, double* quantities, bool apply_sat);
+__host__ __device__ inline int phys_k_host(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
+
+template <typename T>
+static int32_t upload(T** dptr, const std::vector<T>& h) {
+    *dptr = nullptr;
+    if (h.empty()) return SBP_OK;
+    SBP_CUDA(cudaMalloc(dptr, h.size() * sizeof(T)));
+    SBP_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SBP_OK;
+}
+
+// Build device images of G dense N x N operators given column-major host matrices (leading dimension ldd).
+static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd, const double* h_w, int flags) {
+    sbp_ctx* ctx = op->ctx;
+    op->N = N;
+    op->G = G;
+    op->nnz = (int64_t)G * N * N;
+    const bool small = N <= kMaxSmallN && !(flags & SBP_DENSE_FORCE_GEMM);
+    const size_t nn = (size_t)N * N;
+    // row-major table (+ column-major copy for the generic table kernel when small)
+    std::vector<double> rm(G * nn * (small ? 2 : 1));
+    for (int g = 0; g < G; g++) {
+        const double* Dg = h_D + (size_t)g * ldd * N;
+        for (int i = 0; i < N; i++)
+            for (int k = 0; k < N; k++) rm[g * nn + (size_t)i * N + k] = Dg[(size_t)k * ldd + i];
+        if (small)
+            for (int k = 0; k < N; k++)
+                for (int i = 0; i < N; i++) rm[G * nn + g * nn + (size_t)k * N + i] = Dg[(size_t)k * ldd + i];
+    }
+    int32_t rc = upload(&op->d_D, rm);
+    if (rc) return rc;
+    if (h_w) {
+        std::vector<double> w(h_w, h_w + (size_t)G * N);
+        rc = upload(&op->d_w, w);
+        if (rc) return rc;
+    }
+    if (small) {
+        const int NT = (N + 7) / 8, KS = 2 * NT;
+        op->NT = NT;
+        const size_t FR = (size_t)KS * NT * 32;
+        if ((int64_t)(G * FR * 8 + G * KS * 32 + 4096) <= ctx->smem_optin) {
+            std::vector<double> frag(G * FR, 0.0), wfrag;
+            for (int g = 0; g < G; g++) {
+                const double* Dg = h_D + (size_t)g * ldd * N;
+                for (int ks = 0; ks < KS; ks++)
+                    for (int nt = 0; nt < NT; nt++)
+                        for (int lane = 0; lane < 32; lane++) {
+                            const int row = nt * 8 + (lane >> 2), col = phys_k_host(ks, lane & 3);
+                            if (row < N && col < N)
+                                frag[g * FR + ((size_t)ks * NT + nt) * 32 + lane] = Dg[(size_t)col * ldd + row];
+                        }
+            }
+            rc = upload(&op->d_frag, frag);
+            if (rc) return rc;
+            if (h_w) {
+                wfrag.assign((size_t)G * KS * 4, 0.0);
+                for (int g = 0; g < G; g++)
+                    for (int ks = 0; ks < KS; ks++)
+                        for (int t = 0; t < 4; t++) {
+                            const int k = phys_k_host(ks, t);
+                            if (k < N) wfrag[(size_t)g * KS * 4 + ks * 4 + t] = h_w[(size_t)g * N + k];
+                        }
+                rc = upload(&op->d_wfrag, wfrag);
+                if (rc) return rc;
+            }
+            op->variant = SBP_KERNEL_DMMA_SMEM;
+        } else {
+            op->variant = SBP_KERNEL_TABLE;  // table too large for shared memory: generic kernel only
+        }
+    } else {
+        op->variant = SBP_KERNEL_DGEMM_TILED;
+    }
+    return SBP_OK;
+}
+
+static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, const std::vector<int>& col,
+                          const std::vector<double>& val) {
+    const int n_slices = (N + 31) / 32;
+    std::vector<int> slice_ptr(n_slices + 1, 0);
+    int maxw = 0;
+    for (int s = 0; s < n_slices; s++) {
+        int w = 0;
+        for (int r = s * 32; r < std::min(N, s * 32 + 32); r++) w = std::max(w, rowptr[r + 1] - rowptr[r]);
+        slice_ptr[s + 1] = slice_ptr[s] + w;
+        maxw = std::max(maxw, w);
+    }
+    const size_t total = (size_t)slice_ptr[n_slices] * 32;
+    std::vector<int> sc(total);
+    std::vector<double> sv(total, 0.0);
+    for (int s = 0; s < n_slices; s++) {
+        const int w = slice_ptr[s + 1] - slice_ptr[s];
+        for (int l = 0; l < 32; l++) {
+            const int r = s * 32 + l;
+            const int rr = std::min(r, N - 1);
+            const int beg = r < N ? rowptr[r] : 0, cnt = r < N ? rowptr[r + 1] - rowptr[r] : 0;
+            for (int j = 0; j < w; j++) {
+                const size_t at = ((size_t)slice_ptr[s] + j) * 32 + l;
+                if (j < cnt) {
+                    sc[at] = col[beg + j];
+                    sv[at] = val[beg + j];
+                } else {
+                    sc[at] = rr;  // padding: value 0 times a valid column
+                }
+            }
+        }
+    }
+    op->n_slices = n_slices;
+    op->max_row_nnz = maxw;
+    int32_t rc = upload(&op->d_slice_ptr, slice_ptr);
+    if (rc) return rc;
+    rc = upload(&op->d_sell_col, sc);
+    if (rc) return rc;
+    rc = upload(&op->d_sell_val, sv);
+    if (rc) return rc;
+    rc = upload(&op->d_rowptr, rowptr);
+    if (rc) return rc;
+    rc = upload(&op->d_col, col);
+    if (rc) return rc;
+    return upload(&op->d_val, val);
+}
+
+// ---- NCCL through dlopen (no link-time dependency; torch's bundled libnccl is reused when loaded) -----
+struct Id128 {
+    char b[128];
+};
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /*ncclUniqueId by value*/ Id128, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int32_t load_nccl() {
+    if (g_nccl.handle) return SBP_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    SBP_REQUIRE(h != nullptr, SBP_ENCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    SBP_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy, SBP_ENCCL,
+                "libnccl is missing required symbols");
+    g_nccl.handle = h;
+    return SBP_OK;
+}
+
+}  // namespace sbp
+
+using namespace sbp;
+
+extern "C" {
+
+int32_t sbp_version(void) { return 100; }  // 0.1.0
+const char* sbp_last_error(void) { return g_last_error.c_str(); }
+
+int32_t sbp_device_count(int32_t* n) {
+    SBP_REQUIRE(n, SBP_EINVAL, "null output");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *n = c;
+    return SBP_OK;
+}
+
+int32_t sbp_ctx_create(int32_t device, sbp_ctx** out) {
+    SBP_REQUIRE(out, SBP_EINVAL, "null output");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libsbp_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return SBP_ECUDA;
+    }
+    SBP_REQUIRE(device >= 0 && device < count, SBP_EINVAL, "device %d out of range [0,%d)", device, count);
+    SBP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SBP_CUDA(cudaGetDeviceProperties(&prop, device));
+    SBP_REQUIRE(prop.major >= 10, SBP_EUNSUPPORTED,
+                "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    sbp_ctx* ctx = new sbp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = prop.l2CacheSize;
+    ctx->smem_optin = (int64_t)prop.sharedMemPerBlockOptin;
+    ctx->global_bytes = (int64_t)prop.totalGlobalMem;
+    SBP_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    SBP_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    SBP_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int s = 0; s < 2; s++)
+        for (int k = 0; k < 3; k++) SBP_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[s][k], cudaEventDisableTiming));
+    *out = ctx;
+    return SBP_OK;
+}
+
+int32_t sbp_ctx_set_stream(sbp_ctx* ctx, void* cuda_stream) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return SBP_OK;
+}
+int32_t sbp_ctx_get_stream(sbp_ctx* ctx, void** cuda_stream) {
+    SBP_REQUIRE(ctx && cuda_stream, SBP_EINVAL, "null argument");
+    *cuda_stream = ctx->stream;
+    return SBP_OK;
+}
+int32_t sbp_ctx_sync(sbp_ctx* ctx) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SBP_OK;
+}
+int32_t sbp_ctx_destroy(sbp_ctx* ctx) {
+    if (!ctx) return SBP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    for (int s = 0; s < 2; s++) {
+        for (int k = 0; k < 2; k++)
+            if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
+        for (int k = 0; k < 3; k++)
+            if (ctx->pipe_ev[s][k]) cudaEventDestroy(ctx->pipe_ev[s][k]);
+    }
+    cudaStreamDestroy(ctx->own_stream);
+    cudaStreamDestroy(ctx->s_in);
+    cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+    return SBP_OK;
+}
+int32_t sbp_ctx_device_info(sbp_ctx* ctx, int32_t* sm_count, int64_t* l2_bytes, int64_t* smem_optin,
+                            int64_t* global_bytes) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    if (smem_optin) *smem_optin = ctx->smem_optin;
+    if (global_bytes) *global_bytes = ctx->global_bytes;
+    return SBP_OK;
+}
+int64_t sbp_ctx_launch_count(sbp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// ---- memory -------------------------------------------------------------------------------------
+int32_t sbp_malloc(sbp_ctx* ctx, size_t bytes, void** dptr) {
+    SBP_REQUIRE(ctx && dptr, SBP_EINVAL, "null argument");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+    return SBP_OK;
+}
+int32_t sbp_free(sbp_ctx* ctx, void* dptr) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    if (!dptr) return SBP_OK;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    SBP_CUDA(cudaFree(dptr));
+    return SBP_OK;
+}
+int32_t sbp_host_alloc(size_t bytes, void** hptr) {
+    SBP_REQUIRE(hptr, SBP_EINVAL, "null output");
+    SBP_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return SBP_OK;
+}
+int32_t sbp_host_free(void* hptr) {
+    if (hptr) SBP_CUDA(cudaFreeHost(hptr));
+    return SBP_OK;
+}
+int32_t sbp_memcpy_h2d(sbp_ctx* ctx, void* dptr, const void* h_src, size_t bytes) {
+    SBP_REQUIRE(ctx && (bytes == 0 || (dptr && h_src)), SBP_EINVAL, "null argument");
+    SBP_CUDA(cudaMemcpyAsync(dptr, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SBP_OK;
+}
+int32_t sbp_memcpy_d2h(sbp_ctx* ctx, void* h_dst, const void* dptr, size_t bytes) {
+    SBP_REQUIRE(ctx && (bytes == 0 || (dptr && h_dst)), SBP_EINVAL, "null argument");
+    SBP_CUDA(cudaMemcpyAsync(h_dst, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SBP_OK;
+}
+int32_t sbp_memset(sbp_ctx* ctx, void* dptr, int32_t byte, size_t bytes) {
+    SBP_REQUIRE(ctx && dptr, SBP_EINVAL, "null argument");
+    SBP_CUDA(cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
+    return SBP_OK;
+}
+
+// ---- operators ----------------------------------------------------------------------------------
+static sbp_op* new_op(sbp_ctx* ctx, int kind) {
+    sbp_op* op = new sbp_op();
+    op->ctx = ctx;
+    op->kind = kind;
+    return op;
+}
+
+int32_t sbp_op_destroy(sbp_op* op) {
+    if (!op) return SBP_OK;
+    cudaSetDevice(op->ctx->device);
+    cudaStreamSynchronize(op->ctx->stream);
+    void* ptrs[] = {op->d_D,         op->d_frag,     op->d_wfrag,    op->d_w,        op->d_frag_sym, op->d_rowptr,
+                    op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
+                    op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete op;
+    return SBP_OK;
+}
+
+int32_t sbp_op_dense_create(sbp_ctx* ctx, int32_t N, const double* h_D, int32_t ldd, const double* h_w,
+                            double scale, int32_t flags, sbp_op** out) {
+    SBP_REQUIRE(ctx && h_D && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(N >= 1 && ldd >= N, SBP_EDIM, "need N >= 1 and ldd >= N (N=%d, ldd=%d)", N, ldd);
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_op* op = new_op(ctx, SBP_OP_DENSE);
+    op->scale = scale;
+    int32_t rc = build_dense(op, N, 1, h_D, ldd, h_w, flags);
+    if (rc) {
+        sbp_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return SBP_OK;
+}
+
+int32_t sbp_op_table_create(sbp_ctx* ctx, int32_t N, int32_t G, const double* h_D, const double* h_w,
+                            sbp_op** out) {
+    SBP_REQUIRE(ctx && h_D && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(N >= 1 && G >= 1, SBP_EDIM, "need N >= 1 and G >= 1");
+    SBP_REQUIRE(N <= kMaxSmallN, SBP_EUNSUPPORTED, "operator tables support N <= %d (got %d)", kMaxSmallN, N);
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_op* op = new_op(ctx, SBP_OP_TABLE);
+    int32_t rc = build_dense(op, N, G, h_D, N, h_w, 0);
+    if (rc) {
+        sbp_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return SBP_OK;
+}
+
+int32_t sbp_op_sparse_create(sbp_ctx* ctx, int32_t N, const int32_t* h_rowptr, const int32_t* h_col,
+                             const double* h_val, const double* h_w, double scale, sbp_op** out) {
+    SBP_REQUIRE(ctx && h_rowptr && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(N >= 1, SBP_EDIM, "need N >= 1");
+    SBP_REQUIRE(h_rowptr[0] == 0, SBP_EINVAL, "rowptr[0] must be 0");
+    const int nnz = h_rowptr[N];
+    SBP_REQUIRE(nnz == 0 || (h_col && h_val), SBP_EINVAL, "null col/val");
+    for (int r = 0; r < N; r++) SBP_REQUIRE(h_rowptr[r + 1] >= h_rowptr[r], SBP_EINVAL, "rowptr not monotone");
+    for (int j = 0; j < nnz; j++)
+        SBP_REQUIRE(h_col[j] >= 0 && h_col[j] < N, SBP_EINVAL, "column index %d out of range at entry %d", h_col[j], j);
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_op* op = new_op(ctx, SBP_OP_SPARSE);
+    op->N = N;
+    op->nnz = nnz;
+    op->scale = scale;
+    op->variant = SBP_KERNEL_CSR_SMEM;
+    std::vector<int> rp(h_rowptr, h_rowptr + N + 1), col(h_col, h_col + nnz);
+    std::vector<double> val(h_val, h_val + nnz);
+    int32_t rc = build_sell(op, N, rp, col, val);
+    if (!rc && h_w) {
+        std::vector<double> w(h_w, h_w + N);
+        rc = upload(&op->d_w, w);
+    }
+    if (rc) {
+        sbp_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return SBP_OK;
+}
+
+int32_t sbp_op_sparse_from_dense(sbp_ctx* ctx, int32_t N, const double* h_D, int32_t ldd, const double* h_w,
+                                 double scale, sbp_op** out) {
+    SBP_REQUIRE(ctx && h_D && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(N >= 1 && ldd >= N, SBP_EDIM, "need N >= 1 and ldd >= N");
+    std::vector<int> rp(N + 1, 0), col;
+    std::vector<double> val;
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < N; k++) {
+            const double v = h_D[(size_t)k * ldd + i];
+            if (v != 0.0) {
+                col.push_back(k);
+                val.push_back(v);
+            }
+        }
+        rp[i + 1] = (int)col.size();
+    }
+    return sbp_op_sparse_create(ctx, N, rp.data(), col.data(), val.data(), h_w, scale, out);
+}
+
+int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h_b, const double* h_w,
+                                  const int32_t* h_mode, int32_t Nb, const int32_t* h_bnd_node,
+                                  const double* h_bnd_tau, sbp_op** out) {
+    SBP_REQUIRE(ctx && A && h_b && h_w && h_mode && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(A->kind == SBP_OP_DENSE || A->kind == SBP_OP_SPARSE, SBP_EINVAL, "A must be a dense or sparse operator");
+    SBP_REQUIRE(Nb == 0 || (h_bnd_node && h_bnd_tau), SBP_EINVAL, "null boundary lists");
+    const int N = A->N;
+    for (int i = 0; i < N; i++) SBP_REQUIRE(h_mode[i] >= 0 && h_mode[i] <= 2, SBP_EINVAL, "mode[%d]=%d not in {0,1,2}", i, h_mode[i]);
+    for (int i = 0; i < Nb; i++)
+        SBP_REQUIRE(h_bnd_node[i] >= 0 && h_bnd_node[i] < N, SBP_EINVAL, "boundary node %d out of range", h_bnd_node[i]);
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_op* op = new_op(ctx, SBP_OP_ADVECTION2D);
+    op->N = N;
+    op->nnz = A->nnz;
+    op->inner = A;
+    op->Nb = Nb;
+    op->variant = A->variant;
+    std::vector<double> b(h_b, h_b + N), qc(3 * (size_t)N, 0.0);
+    std::vector<int> mode(h_mode, h_mode + N);
+    for (int i = 0; i < N; i++) {
+        qc[i] = h_w[i];
+        qc[N + i] = h_w[i] * h_b[i];  // P*B diagonal (:90,:94-96)
+    }
+    for (int i = 0; i < Nb; i++) qc[2 * (size_t)N + h_bnd_node[i]] += h_bnd_tau[i];  // :98-105
+    int32_t rc = upload(&op->d_b, b);
+    if (!rc) rc = upload(&op->d_mode, mode);
+    if (!rc) rc = upload(&op->d_q_consts, qc);
+    if (!rc) {
+        std::vector<double> w(h_w, h_w + N);
+        rc = upload(&op->d_w, w);
+    }
+    if (rc) {
+        sbp_op_destroy(op);
+        return rc;
+    }
+    *out = op;
+    return SBP_OK;
+}
+
+int32_t sbp_op_advection1d_create(sbp_ctx* ctx, const sbp_op* D, const double* h_a, sbp_op** out) {
+    SBP_REQUIRE(ctx && D && h_a && out, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(D->kind == SBP_OP_DENSE || D->kind == SBP_OP_SPARSE, SBP_EINVAL, "D must be a dense or sparse operator");
+    SBP_REQUIRE(D->d_w != nullptr, SBP_EINVAL, "the 1D advection bundle needs an operator with weights");
+    const int N = D->N;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_op* op = new_op(ctx, SBP_OP_ADVECTION1D);
+    op->N = N;
+    op->nnz = D->nnz;
+    op->inner = D;
+    op->variant = D->variant;
+    bool unit = true;
+    for (int i = 0; i < N; i++) unit = unit && (h_a[i] == 1.0);
+    // D*a on the device (one instance), then w .* (D*a) on the host
+    std::vector<double> a(h_a, h_a + N), w(N), Da(N);
+    double *d_a = nullptr, *d_Da = nullptr;
+    int32_t rc = upload(&d_a, a);
+    if (rc) goto fail;
+    if (cudaMalloc(&d_Da, N * sizeof(double)) != cudaSuccess) {
+        rc = SBP_ENOMEM;
+        goto fail;
+    }
+    rc = sbp_apply(ctx, D, d_Da, d_a, 1, 1.0, 0.0);
+    if (rc) goto fail;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+        cudaMemcpy(Da.data(), d_Da, N * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(w.data(), D->d_w, N * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("advection1d_create: device copy failed");
+        rc = SBP_ECUDA;
+        goto fail;
+    }
+    {
+        std::vector<double> qc(3 * (size_t)N);
+        for (int i = 0; i < N; i++) {
+            qc[i] = w[i];
+            qc[N + i] = w[i] * Da[i];
+            qc[2 * (size_t)N + i] = h_a[i];
+        }
+        rc = upload(&op->d_q_consts, qc);
+        if (rc) goto fail;
+    }
+    if (!unit) {
+        if (D->kind == SBP_OP_DENSE && D->variant == SBP_KERNEL_DMMA_SMEM) {
+            const int KS = 2 * D->NT;
+            std::vector<double> cf((size_t)KS * 4, 0.0);
+            for (int ks = 0; ks < KS; ks++)
+                for (int t = 0; t < 4; t++) {
+                    const int k = phys_k_host(ks, t);
+                    if (k < N) cf[ks * 4 + t] = h_a[k];
+                }
+            rc = upload(&op->d_a, cf);
+        } else if (D->kind == SBP_OP_SPARSE) {
+            rc = upload(&op->d_a, a);
+        } else {
+            set_error("advection1d: variable speed with a large dense operator is not supported");
+            rc = SBP_EUNSUPPORTED;
+        }
+        if (rc) goto fail;
+    }
+    cudaFree(d_a);
+    cudaFree(d_Da);
+    *out = op;
+    return SBP_OK;
+fail:
+    if (d_a) cudaFree(d_a);
+    if (d_Da) cudaFree(d_Da);
+    sbp_op_destroy(op);
+    return rc;
+}
+
+int32_t sbp_op_info(const sbp_op* op, int32_t* kind, int32_t* N, int32_t* G, int64_t* nnz, int32_t* variant) {
+    SBP_REQUIRE(op, SBP_EINVAL, "null op");
+    if (kind) *kind = op->kind;
+    if (N) *N = op->N;
+    if (G) *G = op->G;
+    if (nnz) *nnz = op->nnz;
+    if (variant) *variant = op->variant;
+    return SBP_OK;
+}
+
+// ---- hot path -----------------------------------------------------------------------------------
+static int32_t check_batch(sbp_ctx* ctx, const sbp_op* op, const void* dU, const void* U, int64_t B) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(op->ctx == ctx, SBP_EINVAL, "operator belongs to a different context");
+    SBP_REQUIRE(B >= 0, SBP_EDIM, "negative batch size");
+    SBP_REQUIRE(B == 0 || (dU && U), SBP_EINVAL, "null batch pointer");
+    SBP_REQUIRE(B == 0 || dU != U, SBP_EINVAL, "dU and U must not alias");
+    SBP_REQUIRE((reinterpret_cast<uintptr_t>(dU) & 7) == 0 && (reinterpret_cast<uintptr_t>(U) & 7) == 0, SBP_EINVAL,
+                "batch pointers must be 8-byte aligned");
+    return SBP_OK;
+}
+
+int32_t sbp_apply(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                  double beta) {
+    int32_t rc = check_batch(ctx, op, dU, U, B);
+    if (rc || B == 0) return rc;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    switch (op->kind) {
+        case SBP_OP_DENSE:
+            if (op->variant == SBP_KERNEL_DMMA_SMEM)
+                return launch_dense_small(ctx, op, dU, U, B, alpha, beta, false, nullptr, nullptr);
+            return launch_dense_gemm(ctx, op, dU, U, B, alpha, beta);
+        case SBP_OP_TABLE:
+            if (op->variant == SBP_KERNEL_DMMA_SMEM)
+                return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, nullptr, nullptr);
+            return launch_table_generic(ctx, op, dU, U, B, nullptr, alpha, beta, nullptr, nullptr);
+        case SBP_OP_SPARSE:
+            return launch_sparse(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, 0, nullptr);
+        default:
+            set_error("sbp_apply: operator kind %d is a semidiscretization bundle; use sbp_rhs_*", op->kind);
+            return SBP_EINVAL;
+    }
+}
+
+int32_t sbp_apply_table(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                        const int32_t* op_index, double alpha, double beta, double* energy, double* energy_sum) {
+    int32_t rc = check_batch(ctx, op, dU, U, B);
+    if (rc) return rc;
+    SBP_REQUIRE(op->kind == SBP_OP_TABLE || op->kind == SBP_OP_DENSE, SBP_EINVAL,
+                "sbp_apply_table needs a table or dense operator");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    if (B == 0) {
+        if (energy_sum) SBP_CUDA(cudaMemsetAsync(energy_sum, 0, sizeof(double), ctx->stream));
+        return SBP_OK;
+    }
+    if (op->variant == SBP_KERNEL_DGEMM_TILED) {
+        rc = launch_dense_gemm(ctx, op, dU, U, B, alpha, beta);
+        if (rc || !(energy || energy_sum)) return rc;
+        SBP_REQUIRE(op->d_w, SBP_EINVAL, "energy requested but the operator has no weights");
+        return launch_integrate(ctx, op->d_w, op->N, 1, U, nullptr, B, 1, energy, energy_sum);
+    }
+    if (op_index == nullptr && op->variant == SBP_KERNEL_DMMA_SMEM)
+        return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, energy, energy_sum);
+    return launch_table_generic(ctx, op, dU, U, B, op_index, alpha, beta, energy, energy_sum);
+}
+
+int32_t sbp_integrate(sbp_ctx* ctx, const sbp_op* op, const double* U, const double* V, int64_t B, int32_t mode,
+                      double* out, double* out_sum) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(op->d_w, SBP_EINVAL, "operator has no quadrature weights");
+    SBP_REQUIRE(B >= 0, SBP_EDIM, "negative batch size");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    if (B == 0) {
+        if (out_sum) SBP_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(double), ctx->stream));
+        return SBP_OK;
+    }
+    SBP_REQUIRE(U, SBP_EINVAL, "null U");
+    return launch_integrate(ctx, op->d_w, op->N, op->G, U, V, B, mode, out, out_sum);
+}
+
+int32_t sbp_scale_by_mass_matrix(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, double factor,
+                                 int32_t inverse) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(op->d_w, SBP_EINVAL, "operator has no quadrature weights");
+    SBP_REQUIRE(op->G == 1, SBP_EUNSUPPORTED, "scale_by_mass_matrix on operator tables is not supported");
+    SBP_REQUIRE(B >= 0, SBP_EDIM, "negative batch size");
+    if (B == 0) return SBP_OK;
+    SBP_REQUIRE(U, SBP_EINVAL, "null U");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    return launch_scale(ctx, op->d_w, op->N, U, B, factor, inverse);
+}
+
+int32_t sbp_rhs_advection2d(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, const double* g,
+                            int64_t g_stride, double* quantities) {
+    int32_t rc = check_batch(ctx, op, dU, U, B);
+    if (rc || B == 0) return rc;
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION2D, SBP_EINVAL, "not a 2D advection bundle");
+    SBP_REQUIRE(g != nullptr, SBP_EINVAL, "boundary data g is required");
+    SBP_REQUIRE(g_stride == 0 || g_stride >= op->N, SBP_EDIM, "g_stride must be 0 or >= N");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const sbp_op* A = op->inner;
+    if (A->kind == SBP_OP_SPARSE) return launch_sparse(ctx, A, dU, U, B, -1.0, 0.0, op, g, g_stride, quantities);
+    rc = sbp_apply(ctx, A, dU, U, B, -1.0, 0.0);
+    if (rc) return rc;
+    return launch_adv2d_epilogue(ctx, op, dU, U, B, g, g_stride, quantities, true);
+}
+
+int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                            const double* bc, int64_t bc_stride, double* quantities) {
+    int32_t rc = check_batch(ctx, op, dU, U, B);
+    if (rc || B == 0) return rc;
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION1D, SBP_EINVAL, "not a 1D advection bundle");
+    SBP_REQUIRE(bc != nullptr, SBP_EINVAL, "boundary data bc is required");
+    SBP_REQUIRE(bc_stride == 0 || bc_stride >= 2, SBP_EDIM, "bc_stride must be 0 or >= 2");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const sbp_op* D = op->inner;
+    if (D->kind == SBP_OP_SPARSE)
+        rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a);
+    else if (D->variant == SBP_KERNEL_DMMA_SMEM)
+        rc = launch_dense_small_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, op->d_a);
+    else
+        rc = launch_dense_gemm(ctx, D, dU, U, B, -1.0, 0.0);
+    if (rc) return rc;
+    return launch_adv1d_epilogue(ctx, op, dU, U, B, bc, bc_stride, quantities, true);
+}
+
+int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,
+                     double c) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    SBP_REQUIRE(n >= 0, SBP_EDIM, "negative length");
+    if (n == 0) return SBP_OK;
+    SBP_REQUIRE(Y && X, SBP_EINVAL, "null vector");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    return launch_axpbypcz(ctx, Y, X, Z, n, a, b, c);
+}
+
+// ---- multi-GPU --------------------------------------------------------------------------------------
+int32_t sbp_comm_unique_id(char id[SBP_NCCL_ID_BYTES]) {
+    SBP_REQUIRE(id, SBP_EINVAL, "null id");
+    int32_t rc = load_nccl();
+    if (rc) return rc;
+    int e = g_nccl.GetUniqueId(id);
+    SBP_REQUIRE(e == 0, SBP_ENCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+    return SBP_OK;
+}
+int32_t sbp_comm_init(sbp_ctx* ctx, int32_t nranks, int32_t rank, const char id[SBP_NCCL_ID_BYTES]) {
+    SBP_REQUIRE(ctx && id, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, SBP_EINVAL, "bad rank %d / %d", rank, nranks);
+    int32_t rc = load_nccl();
+    if (rc) return rc;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    Id128 uid;
+    memcpy(uid.b, id, 128);
+    int e = g_nccl.CommInitRank(&ctx->nccl_comm, nranks, uid, rank);
+    SBP_REQUIRE(e == 0, SBP_ENCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+    return SBP_OK;
+}
+int32_t sbp_allreduce_sum(sbp_ctx* ctx, double* dptr, int32_t count) {
+    SBP_REQUIRE(ctx && dptr, SBP_EINVAL, "null argument");
+    SBP_REQUIRE(ctx->nccl_comm, SBP_ENCCL, "communicator not initialised (sbp_comm_init)");
+    int e = g_nccl.AllReduce(dptr, dptr, (size_t)count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl_comm, ctx->stream);
+    SBP_REQUIRE(e == 0, SBP_ENCCL, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+    return SBP_OK;
+}
+int32_t sbp_comm_destroy(sbp_ctx* ctx) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    return SBP_OK;
+}
+
+// ---- host-buffer pipeline -----------------------------------------------------------------------------
+int32_t sbp_apply_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B, double alpha,
+                       double beta, int64_t chunk_instances) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(B >= 0, SBP_EDIM, "negative batch size");
+    if (B == 0) return SBP_OK;
+    SBP_REQUIRE(h_dU && h_U, SBP_EINVAL, "null host buffer");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const int N = op->N;
+    const int G = op->G;
+    if (chunk_instances <= 0) chunk_instances = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)N * 8));
+    // keep chunks a multiple of 128*G so that table periodicity and kernel tiling are preserved
+    const int64_t q = 128 * (int64_t)G;
+    chunk_instances = std::max<int64_t>(q, (chunk_instances / q) * q);
+    chunk_instances = std::min<int64_t>(chunk_instances, ((B + q - 1) / q) * q);
+    const size_t cbytes = (size_t)chunk_instances * N * sizeof(double);
+    if (ctx->pipe_bytes < cbytes) {
+        SBP_CUDA(cudaDeviceSynchronize());
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 2; k++) {
+                if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
+                ctx->pipe_dev[s][k] = nullptr;
+            }
+        ctx->pipe_bytes = 0;
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 2; k++) SBP_CUDA(cudaMalloc(&ctx->pipe_dev[s][k], cbytes));
+        ctx->pipe_bytes = cbytes;
+    }
+    cudaStream_t compute = ctx->stream;
+    // the pipeline must start after work already queued on the compute stream
+    SBP_CUDA(cudaEventRecord(ctx->pipe_ev[0][2], compute));
+    SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[0][2], 0));
+    SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[0][2], 0));
+    int64_t done = 0;
+    int c = 0;
+    enum { EV_IN = 0, EV_COMP = 1, EV_OUT = 2 };
+    bool used[2] = {false, false};
+    while (done < B) {
+        const int s = c & 1;
+        const int64_t nb = std::min<int64_t>(chunk_instances, B - done);
+        const size_t bytes = (size_t)nb * N * sizeof(double);
+        double* dIn = static_cast<double*>(ctx->pipe_dev[s][0]);
+        double* dOut = static_cast<double*>(ctx->pipe_dev[s][1]);
+        if (used[s]) {
+            SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_COMP], 0));  // dIn[s] consumed
+            if (beta != 0.0) SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_OUT], 0));
+        }
+        SBP_CUDA(cudaMemcpyAsync(dIn, h_U + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        if (beta != 0.0) SBP_CUDA(cudaMemcpyAsync(dOut, h_dU + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_IN], ctx->s_in));
+        SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_IN], 0));
+        if (used[s]) SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_OUT], 0));  // dOut[s] drained
+        int32_t rc = sbp_apply(ctx, op, dOut, dIn, nb, alpha, beta);
+        if (rc) return rc;
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_COMP], compute));
+        SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[s][EV_COMP], 0));
+        SBP_CUDA(cudaMemcpyAsync(h_dU + done * N, dOut, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_OUT], ctx->s_out));
+        used[s] = true;
+        done += nb;
+        c++;
+    }
+    SBP_CUDA(cudaStreamSynchronize(ctx->s_out));
+    SBP_CUDA(cudaStreamSynchronize(compute));
+    return SBP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,110 @@
+// common.cuh -- internal structs and error plumbing of libsbp_b200.so
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cuda_runtime.h>
+#include "../../include/sbp_b200.h"
+
+namespace sbp {
+
+void set_error(const char* fmt, ...);
+
+#define SBP_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            sbp::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return (e_ == cudaErrorMemoryAllocation) ? SBP_ENOMEM : SBP_ECUDA;                    \
+        }                                                                                         \
+    } while (0)
+
+#define SBP_REQUIRE(cond, code, ...)     \
+    do {                                 \
+        if (!(cond)) {                   \
+            sbp::set_error(__VA_ARGS__); \
+            return (code);               \
+        }                                \
+    } while (0)
+
+constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
+
+}  // namespace sbp
+
+struct sbp_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // stream launches go to (own_stream or caller-provided)
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams for the host-buffer pipeline
+    int sm_count = 0;
+    int64_t l2_bytes = 0;
+    int64_t smem_optin = 0;
+    int64_t global_bytes = 0;
+    int64_t launches = 0;
+    double* scratch = nullptr;  // per-CTA partial sums for deterministic batch reductions
+    size_t scratch_doubles = 0;
+    // host pipeline staging
+    void* pipe_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][in/out]
+    size_t pipe_bytes = 0;
+    cudaEvent_t pipe_ev[2][3] = {};
+    void* nccl_comm = nullptr;
+};
+
+struct sbp_op {
+    int kind = 0;
+    int N = 0;
+    int G = 1;
+    int64_t nnz = 0;
+    int variant = 0;
+    sbp_ctx* ctx = nullptr;
+    double scale = 1.0;
+    // dense / table
+    double* d_D = nullptr;     // G matrices, ROW-major N x N each (row i contiguous in k), scale NOT folded
+    double* d_frag = nullptr;  // DMMA B-fragment order, G * (KS*NT*32) doubles (small N only)
+    double* d_wfrag = nullptr; // weights in A-fragment k order, G * (KS*4) doubles
+    double* d_w = nullptr;     // G*N weights (or nullptr)
+    int NT = 0;                // n-tiles of 8 rows (small path)
+    bool sym = false;          // centro-antisymmetric (even/odd split available)
+    double* d_frag_sym = nullptr;
+    // sparse (SELL-32 slices)
+    int* d_rowptr = nullptr;
+    int* d_col = nullptr;
+    double* d_val = nullptr;
+    int n_slices = 0;
+    int* d_slice_ptr = nullptr;  // n_slices+1 offsets (in units of 32-wide columns)
+    int* d_sell_col = nullptr;
+    double* d_sell_val = nullptr;
+    int max_row_nnz = 0;
+    // advection bundles
+    const sbp_op* inner = nullptr;
+    double* d_b = nullptr;
+    int* d_mode = nullptr;
+    int Nb = 0;
+    int* d_bnd_node = nullptr;
+    double* d_bnd_tau = nullptr;
+    double* d_a = nullptr;
+    double* d_q_consts = nullptr;  // per-node constants for the analysis quantities
+};
+
+namespace sbp {
+// kernel-family launchers (each in its own .cu)
+int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                           double beta, bool periodic_table, double* energy, double* energy_sum);
+int32_t launch_table_generic(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
+                             const int32_t* op_index, double alpha, double beta, double* energy, double* energy_sum);
+int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                          double beta);
+int32_t launch_sparse(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                      double beta, const sbp_op* adv, const double* g, int64_t g_stride, double* quantities);
+int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V, int64_t B,
+                         int mode, double* out, double* out_sum);
+int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t B, double factor, int inverse);
+int32_t launch_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,
+                        double c);
+int32_t launch_sum_partials(sbp_ctx* ctx, const double* partials, int n, double* out);
+int32_t launch_adv2d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B,
+                              const double* g, int64_t g_stride, double* quantities, bool apply_sat);
+int32_t launch_adv1d(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B, const double* bc,
+                     int64_t bc_stride, double* quantities);
+int32_t ensure_scratch(sbp_ctx* ctx, size_t doubles);
+}  // namespace sbp

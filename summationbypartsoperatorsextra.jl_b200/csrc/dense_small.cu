@@ -1,0 +1,289 @@
+// dense_small.cu -- K1/K4: batched apply of a small dense operator (N <= 128) or a periodic table of
+// such operators, operator fragments resident in shared memory, FP64 tensor-core (DMMA.8x8x4) tiles.
+//
+// Math per instance (src/polynomialbases_operators.jl:148, src/subcell_operators.jl:279, upstream
+// MatrixDerivativeOperator):      y = alpha' * D u + beta * y ,  alpha' = alpha*scale
+// Batched as a GEMM with the INSTANCES on the M axis:   Y[inst][i] = sum_k U[inst][k] * D[i][k]
+//   A operand (row-major 8x4 fragments) = 8 instances x 4 nodes straight from the batch array
+//                                          (instance-contiguous layout == "row-major" A)
+//   B operand (col-major 4x8 fragments) = D^T, pre-permuted on the host into fragment order and
+//                                          staged once per CTA into shared memory with a TMA bulk copy
+//   C fragment: a lane ends up with 2 consecutive output nodes of one instance -> 128-bit stores.
+// The contraction order is free, so one 128-bit load (nodes 8kp+2t, 8kp+2t+1) feeds two k-steps.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sbp {
+
+struct DenseSmallParams {
+    const double* __restrict__ U;
+    double* __restrict__ dU;
+    const double* __restrict__ frag;   // G * KS*NT*32
+    const double* __restrict__ wfrag;  // G * KS*4  (weights in A-fragment k order) or nullptr
+    const double* __restrict__ cfrag;  // KS*4 column scaling (a .* u of the 1D advection) or nullptr
+    int N;
+    int G;
+    long long B;
+    double alpha;
+    double beta;
+    double* energy;   // per instance or nullptr
+    double* partial;  // per-CTA energy partial sums or nullptr
+};
+
+// physical node index of logical (k-step ks, lane-in-group t)
+__host__ __device__ __forceinline__ int phys_k(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
+
+template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE>
+__global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams p) {
+    constexpr int KS = 2 * NT;
+    constexpr int FRAG = KS * NT * 32;
+    constexpr int WARPS = THREADS / 32;
+    extern __shared__ __align__(128) double smem[];
+    __shared__ uint64_t bar;
+    __shared__ double warp_part[WARPS];
+
+    double* s_frag = smem;                          // G*FRAG
+    double* s_wfrag = smem + (size_t)p.G * FRAG;    // G*KS*4 (if ENERGY)
+    double* s_cfrag = s_wfrag + (ENERGY ? p.G * KS * 4 : 0);
+
+    // ---- stage the operator once per CTA: TMA bulk copies tracked by one mbarrier ----
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = (uint32_t)((size_t)p.G * FRAG * sizeof(double));
+        mbar_arrive_expect_tx(&bar, total);
+        uint32_t off = 0;
+        while (off < total) {
+            uint32_t n = total - off < 32768u ? total - off : 32768u;
+            bulk_g2s(reinterpret_cast<char*>(s_frag) + off, reinterpret_cast<const char*>(p.frag) + off, n, &bar);
+            off += n;
+        }
+    }
+    if (ENERGY)
+        for (int i = threadIdx.x; i < p.G * KS * 4; i += THREADS) s_wfrag[i] = p.wfrag[i];
+    if (CSCALE)
+        for (int i = threadIdx.x; i < KS * 4; i += THREADS) s_cfrag[i] = p.cfrag[i];
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int N = p.N, G = p.G;
+    const long long B = p.B;
+    const long long slots = (B + G - 1) / G;  // instance b = slot*G + gi
+    const long long ntiles = (slots + 8 * MT - 1) / (8 * MT);
+    const double alpha = p.alpha, beta = p.beta;
+    double e_acc = 0.0;
+
+    for (long long tile = (long long)blockIdx.x * WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * WARPS) {
+        for (int gi = 0; gi < G; gi++) {
+            // ---- A fragments: 8*MT instances, all N nodes, straight from global memory ----
+            double a[MT][KS];
+            long long inst[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const long long slot = tile * (8 * MT) + mt * 8 + g;
+                inst[mt] = slot * G + gi;
+                const bool valid = inst[mt] < B;
+                const double* up = p.U + inst[mt] * N + 2 * t;
+#pragma unroll
+                for (int kp = 0; kp < NT; kp++) {
+                    if (FULL) {
+                        double2 v = valid ? ldg_stream2(up + 8 * kp) : make_double2(0.0, 0.0);
+                        a[mt][2 * kp] = v.x;
+                        a[mt][2 * kp + 1] = v.y;
+                    } else {
+                        const int k0 = 8 * kp + 2 * t;
+                        a[mt][2 * kp] = (valid && k0 < N) ? ldg_stream1(up + 8 * kp) : 0.0;
+                        a[mt][2 * kp + 1] = (valid && k0 + 1 < N) ? ldg_stream1(up + 8 * kp + 1) : 0.0;
+                    }
+                }
+            }
+            // ---- fused discrete energy  u' P u  (warp-shuffle reduction over the 4 lanes of a group) ----
+            if (ENERGY) {
+                const double* wf = s_wfrag + gi * KS * 4;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    double e = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) e = fma(wf[ks * 4 + t] * a[mt][ks], a[mt][ks], e);
+                    e += __shfl_xor_sync(0xffffffffu, e, 1);
+                    e += __shfl_xor_sync(0xffffffffu, e, 2);
+                    if (t == 0 && inst[mt] < B) {
+                        if (p.energy) p.energy[inst[mt]] = e;
+                        e_acc += e;
+                    }
+                }
+            }
+            if (CSCALE) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) a[mt][ks] *= s_cfrag[ks * 4 + t];
+            }
+            // ---- DMMA: C[mt][nt] += A[mt][ks] * Bfrag[ks][nt] ----
+            double c[MT][NT][2];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+            const double* bf = s_frag + (size_t)gi * FRAG + lane;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    const double b = bf[(ks * NT + nt) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt][ks], b);
+                }
+            }
+            // ---- epilogue: lane owns nodes (8nt+2t, 8nt+2t+1) of instance g of each m-tile ----
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                if (inst[mt] >= B) continue;
+                double* yp = p.dU + inst[mt] * N + 2 * t;
+#pragma unroll
+                for (int nt = 0; nt < NT; nt++) {
+                    double y0 = alpha * c[mt][nt][0], y1 = alpha * c[mt][nt][1];
+                    if (FULL) {
+                        if (beta != 0.0) {
+                            const double2 o = *reinterpret_cast<const double2*>(yp + 8 * nt);
+                            y0 = fma(beta, o.x, y0);
+                            y1 = fma(beta, o.y, y1);
+                        }
+                        stg_stream2(yp + 8 * nt, y0, y1);
+                    } else {
+                        const int r0 = 8 * nt + 2 * t;
+                        if (r0 < N) {
+                            if (beta != 0.0) y0 = fma(beta, yp[8 * nt], y0);
+                            stg_stream1(yp + 8 * nt, y0);
+                        }
+                        if (r0 + 1 < N) {
+                            if (beta != 0.0) y1 = fma(beta, yp[8 * nt + 1], y1);
+                            stg_stream1(yp + 8 * nt + 1, y1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (ENERGY && p.partial) {
+        e_acc = warp_sum(e_acc);
+        if (lane == 0) warp_part[warp] = e_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < WARPS; w++) s += warp_part[w];
+            p.partial[blockIdx.x] = s;
+        }
+    }
+}
+
+template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE>
+static int32_t launch_variant(sbp_ctx* ctx, const DenseSmallParams& p, double* energy_sum) {
+    constexpr int KS = 2 * NT;
+    auto kern = k_dense_small<NT, MT, THREADS, FULL, ENERGY, CSCALE>;
+    size_t smem = (size_t)p.G * KS * NT * 32 * 8 + (ENERGY ? (size_t)p.G * KS * 4 * 8 : 0) + (CSCALE ? KS * 4 * 8 : 0);
+    SBP_REQUIRE((int64_t)smem <= ctx->smem_optin - 1024, SBP_EUNSUPPORTED,
+                "operator table needs %zu bytes of shared memory (> %lld available)", smem,
+                (long long)ctx->smem_optin);
+    SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const long long slots = (p.B + p.G - 1) / p.G;
+    const long long ntiles = (slots + 8 * MT - 1) / (8 * MT);
+    long long want = (ntiles + (THREADS / 32) - 1) / (THREADS / 32);
+    int grid = (int)std::min<long long>((long long)ctx->sm_count * per_sm, std::max<long long>(want, 1));
+    DenseSmallParams q = p;
+    if (ENERGY && energy_sum) {
+        int32_t rc = ensure_scratch(ctx, grid);
+        if (rc) return rc;
+        q.partial = ctx->scratch;
+    }
+    kern<<<grid, THREADS, smem, ctx->stream>>>(q);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    if (ENERGY && energy_sum) return launch_sum_partials(ctx, ctx->scratch, grid, energy_sum);
+    return SBP_OK;
+}
+
+template <int NT>
+static int32_t dispatch_nt(sbp_ctx* ctx, const DenseSmallParams& p, bool full, bool energy, bool cscale,
+                           double* energy_sum) {
+    // m-tiles per warp iteration: keep ~64 accumulator doubles per lane at most
+    constexpr int MT = (NT <= 2) ? 4 : (NT <= 8 ? 2 : 1);
+    constexpr int TH = 128;
+#define SBP_DS(F, E, C) return launch_variant<NT, MT, TH, F, E, C>(ctx, p, energy_sum)
+    if (full) {
+        if (energy) {
+            if (cscale) SBP_DS(true, true, true);
+            SBP_DS(true, true, false);
+        }
+        if (cscale) SBP_DS(true, false, true);
+        SBP_DS(true, false, false);
+    }
+    if (energy) {
+        if (cscale) SBP_DS(false, true, true);
+        SBP_DS(false, true, false);
+    }
+    if (cscale) SBP_DS(false, false, true);
+    SBP_DS(false, false, false);
+#undef SBP_DS
+}
+
+int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                              double beta, double* energy, double* energy_sum, const double* cfrag) {
+    DenseSmallParams p;
+    p.U = U;
+    p.dU = dU;
+    p.frag = op->d_frag;
+    p.wfrag = op->d_wfrag;
+    p.cfrag = cfrag;
+    p.N = op->N;
+    p.G = op->G;
+    p.B = B;
+    p.alpha = alpha * op->scale;
+    p.beta = beta;
+    p.energy = energy;
+    p.partial = nullptr;
+    const bool want_energy = (energy != nullptr) || (energy_sum != nullptr);
+    SBP_REQUIRE(!want_energy || op->d_wfrag, SBP_EINVAL, "energy requested but the operator has no weights");
+    const bool full = (op->N == op->NT * 8) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
+    const bool cs = cfrag != nullptr;
+    switch (op->NT) {
+#define SBP_CASE(n) \
+    case n:         \
+        return dispatch_nt<n>(ctx, p, full, want_energy, cs, energy_sum);
+        SBP_CASE(1)
+        SBP_CASE(2)
+        SBP_CASE(3)
+        SBP_CASE(4)
+        SBP_CASE(5)
+        SBP_CASE(6)
+        SBP_CASE(7)
+        SBP_CASE(8)
+        SBP_CASE(9)
+        SBP_CASE(10)
+        SBP_CASE(11)
+        SBP_CASE(12)
+        SBP_CASE(13)
+        SBP_CASE(14)
+        SBP_CASE(15)
+        SBP_CASE(16)
+#undef SBP_CASE
+    }
+    set_error("dense_small: unsupported N=%d", op->N);
+    return SBP_EUNSUPPORTED;
+}
+
+int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                           double beta, bool /*periodic_table*/, double* energy, double* energy_sum) {
+    return launch_dense_small_ex(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, nullptr);
+}
+
+}  // namespace sbp

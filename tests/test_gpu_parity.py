@@ -1,0 +1,443 @@
+"""GPU parity tests (run with `-m gpu` on a B200): every hot-path entry point of libsbp_b200.so, called through
+the C ABI via the host mirror, against the CPU oracle on the same seeded inputs.
+
+Tolerance (north_star): Float64, per instance  max_i |y_gpu - y_ref| / max_i |y_ref| <= 1e-12.
+The summation order differs from OpenBLAS, so bitwise equality is not expected; the extended-precision truth
+is used to show the GPU error is of the size of the reference BLAS's own rounding error.
+"""
+import numpy as np
+import pytest
+
+import sbp_b200 as S
+from oracle import sbp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = S.Context(0)
+    yield c
+    c.close()
+
+
+def rel_err(Y, Yref):
+    """per-instance norm-wise relative error, max over the batch"""
+    Y, Yref = np.atleast_2d(Y), np.atleast_2d(Yref)
+    scale = np.max(np.abs(Yref), axis=1)
+    scale[scale == 0] = 1.0
+    return float(np.max(np.max(np.abs(Y - Yref), axis=1) / scale))
+
+
+def rand_batch(B, N, seed=0):
+    return np.random.default_rng(seed).uniform(-1, 1, (B, N))
+
+
+# ---- K1: small dense operators (DMMA, smem-resident fragments) -----------------------------------------------
+@pytest.mark.parametrize("N", [2, 3, 5, 7, 8, 16, 24, 33, 64, 101, 128])
+@pytest.mark.parametrize("B", [1, 37, 4099])
+def test_apply_polynomialbases(ctx, N, B):
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -2.0, 1.4, N)
+    Do = O.PolynomialBasesOperator("LobattoLegendre", -2.0, 1.4, N)
+    U = rand_batch(B, N, seed=N + B)
+    u = ctx.upload(U)
+    du = D * u
+    assert du.shape == (B, N)
+    Yref = O.apply_batch(Do.matrix(), U)
+    assert rel_err(du.to_host(), Yref) <= TOL
+    # error against the extended-precision truth is no worse than ~ the CPU BLAS's own
+    Yl = np.asarray(O.apply_batch_longdouble(Do.matrix(), U), dtype=np.float64)
+    assert rel_err(du.to_host(), Yl) <= max(4 * rel_err(Yref, Yl), 1e-14)
+    info = D.device_op(ctx).info()
+    assert info["kernel"] == "dmma_smem" and info["N"] == N
+
+
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (2.5, 0.0), (1.0, 1.0), (-0.5, 3.0), (0.0, 1.0)])
+@pytest.mark.parametrize("N", [7, 64])
+def test_apply_alpha_beta(ctx, N, alpha, beta):
+    D = S.PolynomialBasesDerivativeOperator(S.GaussLegendre, -1.0, 3.0, N)
+    Do = O.PolynomialBasesOperator("GaussLegendre", -1.0, 3.0, N)
+    B = 1001
+    U, Y0 = rand_batch(B, N, 1), rand_batch(B, N, 2)
+    u, du = ctx.upload(U), ctx.upload(Y0)
+    S.mul_(du, D, u, alpha, beta)
+    Yref = O.apply_batch(Do.matrix(), U, alpha, beta, Y0)
+    assert rel_err(du.to_host(), Yref) <= TOL
+
+
+def test_beta_zero_ignores_nan_in_dest(ctx):
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, 16)
+    U = rand_batch(64, 16)
+    du = ctx.upload(np.full((64, 16), np.nan))
+    S.mul_(du, D, ctx.upload(U))
+    assert np.all(np.isfinite(du.to_host()))
+
+
+@pytest.mark.parametrize("basis", ["LobattoLegendre", "GaussLegendre", "GaussRadauLeft", "GaussRadauRight"])
+@pytest.mark.parametrize("p", [2, 4, 6])
+def test_exactness_known_answer(ctx, basis, p):
+    """test/test_polynomialbases_operators.jl:34-38 on the device: D * x^k == k x^(k-1), atol 1e-12."""
+    N = p + 1
+    D = S.polynomialbases_derivative_operator(getattr(S, basis), xmin=-2.0, xmax=1.4, N=N)
+    x = D.grid
+    F = np.stack([x**k for k in range(N)])
+    dF = np.stack([k * x ** (k - 1) if k else np.zeros(N) for k in range(N)])
+    out = (D * ctx.upload(F)).to_host()
+    assert np.max(np.abs(out - dF)) <= 1e-12
+    # integrate / scale_by_mass_matrix round trip (:49-56)
+    u = np.sin(np.pi * x)
+    du = ctx.upload(u)
+    integ = S.integrate(S.identity, du, D)
+    S.scale_by_mass_matrix_(du, D)
+    assert abs(integ - du.to_host().sum()) < 1e-13
+    S.scale_by_inverse_mass_matrix_(du, D)
+    assert np.max(np.abs(du.to_host()[0] - u)) < 1e-12
+    with pytest.raises(S.DimensionMismatch):
+        S.scale_by_mass_matrix_(ctx.upload(np.ones(N + 1)), D)
+    with pytest.raises(S.ArgumentError):
+        S.mul_(ctx.upload(np.ones(N + 1)), D, ctx.upload(np.ones(N + 1)))
+
+
+def test_empty_batch(ctx):
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, 16)
+    u = S.DeviceBatch.empty(ctx, 0, 16)
+    du = D * u
+    assert du.to_host().shape == (0, 16)
+
+
+# ---- K6: large dense operator (tiled DMMA DGEMM) ---------------------------------------------------------------
+@pytest.mark.parametrize("N,B", [(130, 300), (200, 129), (520, 1000), (515, 77)])
+def test_apply_large_dense(ctx, N, B):
+    rng = np.random.default_rng(N)
+    Sk = rng.normal(size=(N, N))
+    Sk = Sk - Sk.T
+    w = rng.uniform(0.5, 1.5, N)
+    w *= 4.0 / w.sum()
+    Bd = np.zeros(N)
+    Bd[: N // 16] = rng.normal(size=N // 16)
+    Dm = (Sk + np.diag(Bd) / 2) / w[:, None]
+    D = S.MatrixDerivativeOperator(0.0, 1.0, np.linspace(0, 1, N), w, Dm, storage="dense")
+    U = rand_batch(B, N, 5)
+    du = D * ctx.upload(U)
+    assert D.device_op(ctx).info()["kernel"] == "dgemm_tiled"
+    assert rel_err(du.to_host(), O.apply_batch(Dm, U)) <= TOL
+    Y0 = rand_batch(B, N, 6)
+    dv = ctx.upload(Y0)
+    S.mul_(dv, D, ctx.upload(U), -1.5, 0.25)
+    assert rel_err(dv.to_host(), O.apply_batch(Dm, U, -1.5, 0.25, Y0)) <= TOL
+
+
+# ---- K2: structurally sparse operators ---------------------------------------------------------------------------
+@pytest.mark.parametrize("order,N", [(2, 101), (4, 101), (4, 400), (2, 1500)])
+@pytest.mark.parametrize("B", [1, 19, 1030])
+def test_apply_sparse_1d(ctx, order, N, B):
+    D = S.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
+    D.storage = "sparse"
+    Do = O.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
+    U = rand_batch(B, N, 3)
+    du = D * ctx.upload(U)
+    assert D.device_op(ctx).info()["kernel"] == "csr_smem"
+    assert rel_err(du.to_host(), O.apply_batch(Do.matrix(), U)) <= TOL
+    Y0 = rand_batch(B, N, 4)
+    dv = ctx.upload(Y0)
+    S.mul_(dv, D, ctx.upload(U), 0.5, -2.0)
+    assert rel_err(dv.to_host(), O.apply_batch(Do.matrix(), U, 0.5, -2.0, Y0)) <= TOL
+
+
+def test_sparse_equals_dense_path(ctx):
+    """skipping structural zeros is exact for finite inputs: sparse and dense kernels agree to rounding"""
+    N = 96
+    Dd = S.mattsson_nordstrom_2004(4, -1.0, 1.0, N)
+    Ds = S.mattsson_nordstrom_2004(4, -1.0, 1.0, N)
+    Dd.storage, Ds.storage = "dense", "sparse"
+    U = rand_batch(513, N, 9)
+    u = ctx.upload(U)
+    assert rel_err((Ds * u).to_host(), (Dd * u).to_host()) <= 1e-14
+
+
+def _scattered_mfsbp(n1=12, seed=0, jitter=True):
+    """tensor-product MN2004 operator values on a (jittered) grid, sparsified by ellipsoid neighbourhoods plus random
+    entries on the pattern -- exercises general sparse Dx/Dy with duplicated-corner boundary lists."""
+    D1 = S.mattsson_nordstrom_2004(2, -1.0, 1.0, n1)
+    D2 = S.tensor_product_operator_2D(D1)
+    rng = np.random.default_rng(seed)
+    nodes = D2.grid.copy()
+    if jitter:
+        dx = 2.0 / (n1 - 1)
+        interior = np.ones(D2.N, bool)
+        interior[np.unique(D2.boundary_indices)] = False
+        nodes[interior] += dx / 6 * (1 - 2 * rng.uniform(size=(interior.sum(), 2)))
+    lx, ly = 2.6 * 2.0 / (n1 - 1), 1.6 * 2.0 / (n1 - 1)
+    Ds = []
+    for dim, lengths in ((0, (lx, ly)), (1, (ly, lx))):
+        pat = S.neighborhood_sparsity_pattern(nodes, lengths)
+        pat = pat | pat.T | np.eye(D2.N, dtype=bool)
+        Dd = D2.Ds[dim].copy()
+        extra = pat & (Dd == 0)
+        Dd[extra] = 0.05 * rng.normal(size=extra.sum())
+        Ds.append(Dd)
+    return S.MultidimensionalMatrixDerivativeOperator(nodes, D2.boundary_indices, D2.normals, D2.weights(),
+                                                      D2.weights_boundary, Ds, 2, "test", corners=D2.corners)
+
+
+def _oracle_md(D):
+    return O.MultidimensionalOperator(D.grid, D.boundary_indices, D.normals, D.weights(), D.weights_boundary, D.Ds)
+
+
+@pytest.mark.parametrize("storage", ["sparse", "dense"])
+@pytest.mark.parametrize("n1", [6, 12, 20])
+def test_apply_mfsbp_directions(ctx, n1, storage):
+    D = _scattered_mfsbp(n1)
+    D.storage = storage
+    for d in D._dirs:
+        d.storage = storage
+    U = rand_batch(257, D.N, 11)
+    u = ctx.upload(U)
+    for dim in (0, 1):
+        assert rel_err((D[dim] * u).to_host(), O.apply_batch(D.Ds[dim], U)) <= TOL
+
+
+# ---- K3: fused 2D advection RHS with SAT + analysis quantities -------------------------------------------------
+@pytest.mark.parametrize("storage", ["sparse", "dense"])
+@pytest.mark.parametrize("a", [(1.0, 1.0), (1.0, -0.5), (-0.3, 0.0)])
+def test_rhs_advection2d(ctx, storage, a):
+    D = _scattered_mfsbp(12, seed=1)
+    u0 = lambda x: np.exp(-30 * (x[0] ** 2 + x[1] ** 2))
+    g = lambda x, t: u0((x[0] - a[0] * t, x[1] - a[1] * t)) + 0.1 * np.sin(3 * x[0] - x[1] + t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, g, storage=storage)
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    B, t = 133, 0.37
+    U = rand_batch(B, D.N, 21)
+    U[0] = [u0(x) for x in D.grid]  # the physical initial condition as instance 0
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, D.N)
+    assert semi(du, u, None, t) is None
+    dU = du.to_host()
+    Q = S.analyze_quantities(semi, du, u, None, t)
+    assert np.array_equal(du.to_host(), dU)  # analysis re-evaluates the same RHS
+    ref = np.empty_like(U)
+    qref = np.empty((B, 7))
+    for b in range(B):
+        ref[b] = semio.rhs(U[b], t)
+        qref[b] = semio.analyze_quantities(ref[b], U[b])
+    assert rel_err(dU, ref) <= TOL
+    # quantities are sums with cancellation: compare against the magnitude of the summed terms
+    P = D.weights()
+    mag = np.stack([np.abs(U) @ P, np.abs(ref) @ P, np.abs(ref) @ P + 1, (U**2) @ P, np.abs(ref * U) @ P,
+                    np.abs(ref * U) @ P + 1, np.abs(ref * U) @ P + 1], axis=1)
+    assert np.max(np.abs(Q - qref) / mag) <= 1e-12
+
+
+def test_rhs_advection2d_per_instance_boundary_data(ctx):
+    D = _scattered_mfsbp(8, seed=2)
+    a = (0.7, 1.0)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, lambda x, t: 0.0, storage="sparse")
+    B = 65
+    U, G = rand_batch(B, D.N, 1), rand_batch(B, D.N, 2)
+    u, g, du = ctx.upload(U), ctx.upload(G), S.DeviceBatch.empty(ctx, B, D.N)
+    semi(du, u, None, 0.0, g=g)
+    out = du.to_host()
+    for b in (0, 17, 64):
+        semio = O.AdvectionSemi2D(_oracle_md(D), a, None, D.corners)
+        semio.bc = lambda node, t, b=b: G[b, int(np.argmin(np.sum((D.grid - node) ** 2, axis=1)))]
+        assert rel_err(out[b], semio.rhs(U[b], 0.0)) <= TOL
+
+
+# ---- 1D advection (config 1) --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("storage", ["sparse", "dense"])
+@pytest.mark.parametrize("speed", ["unit", "variable", "negative"])
+def test_rhs_advection1d(ctx, storage, speed):
+    N = 101
+    D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    D.storage = storage
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    afun = {"unit": lambda x: 1.0, "variable": lambda x: 1.0 + 0.5 * np.sin(3 * x), "negative": lambda x: -0.8}[speed]
+    u0 = lambda x: np.tanh(50 * (x - 0.1))
+    lbc, rbc = (lambda t: u0(-t)), (lambda t: 0.3 * np.cos(t))
+    semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, afun, False, lbc, rbc)
+    semio = O.AdvectionSemi1D(Do, afun, lbc, rbc)
+    B, t = 77, 0.2
+    U = rand_batch(B, N, 8)
+    U[0] = u0(D.grid)
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, N)
+    semi(du, u, None, t)
+    dU = du.to_host()
+    ref = np.stack([semio.rhs(U[b], t) for b in range(B)])
+    assert rel_err(dU, ref) <= TOL
+    Q = S.analyze_quantities(semi, du, u, None, t)
+    qref = np.stack([semio.analyze_quantities(ref[b], U[b], t) for b in range(B)])
+    P = Do.weights()
+    mag = np.max(np.abs(ref), axis=1, keepdims=True) * np.max(np.abs(U), axis=1, keepdims=True) * P.sum() + 1.0
+    assert np.max(np.abs(Q - qref) / mag) <= 1e-12
+
+
+def test_ssprk53_example_run(ctx):
+    """examples/RBF_FSBP_advection.jl:9-51 with a closed-form banded SBP operator standing in for the RBF operator:
+    N = 101, a = 1, u0 = tanh(50(x-0.1)), SSPRK53, dt = 0.009, tspan = (0, 0.5), AnalysisCallback(dt = 0.01)."""
+    N = 101
+    D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    D.storage = "sparse"
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    u0 = lambda x: np.tanh(50 * (x - 0.1))
+    lbc, rbc = (lambda t: u0(0.0 - t)), (lambda t: 0.0)
+    semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, lambda x: 1.0, False, lbc, rbc)
+    semio = O.AdvectionSemi1D(Do, lambda x: 1.0, lbc, rbc)
+    cb = S.AnalysisCallback(semi, dt=0.01)
+    prob = S.semidiscretize(u0, semi, (0.0, 0.5), ctx=ctx, batch=3)
+    dt = 0.9 * 0.01
+    uend = S.solve_ssprk53(prob, dt, callback=cb).to_host()
+    u, t = u0(Do.grid), 0.0
+    while t < 0.5 - 1e-14:
+        h = min(dt, 0.5 - t)
+        u = O.ssprk53_step(semio.rhs, u, t, h)
+        t += h
+    assert rel_err(uend, np.tile(u, (3, 1))) <= 1e-11  # ~56 steps x 5 stages of rounding differences
+    assert len(S.tstops(cb)) >= 50 and S.quantities(cb)[0].shape == (3, 7)
+    assert np.max(np.abs(uend[0] - np.tanh(50 * (Do.grid - 0.5 - 0.1)))) < 0.2
+
+
+# ---- K4: operator table (sub-cell operators with varying split point) + fused energy ------------------------
+def _subcell_table(N=16, couplings=("no", "central")):
+    ops, ops_o = [], []
+    NLs = [4, 5, 6, 7, 8, 9, 10, 11]
+    for i, NL in enumerate(NLs):
+        x_M = -1.0 + 2.0 * NL / N
+        c = couplings[i % len(couplings)]
+        ops.append(S.couple_subcell(S.legendre_derivative_operator(-1.0, x_M, NL),
+                                    S.legendre_derivative_operator(x_M, 1.0, N - NL), x_M, c))
+        ops_o.append(O.couple_subcell(O.legendre_derivative_operator(-1.0, x_M, NL),
+                                      O.legendre_derivative_operator(x_M, 1.0, N - NL), x_M, c))
+    return ops, ops_o
+
+
+@pytest.mark.parametrize("B", [1, 8, 1000, 16411])
+def test_subcell_table_periodic_with_energy(ctx, B):
+    ops, ops_o = _subcell_table()
+    table = S.OperatorTable(ops)
+    U = rand_batch(B, 16, 13)
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, 16)
+    _, E, Esum = table.mul_(du, u, energy=True, energy_sum=True)
+    out = du.to_host()
+    ref = np.stack([ops_o[b % 8].mul(U[b]) for b in range(B)])
+    eref = np.array([ops_o[b % 8].integrate(np.square, U[b]) for b in range(B)])
+    assert rel_err(out, ref) <= TOL
+    assert np.max(np.abs(E - eref) / eref) <= TOL
+    assert abs(Esum - eref.sum()) <= TOL * eref.sum()
+    assert table.device_op(ctx).info()["kernel"] == "dmma_smem"
+
+
+def test_subcell_table_indexed(ctx):
+    ops, ops_o = _subcell_table()
+    table = S.OperatorTable(ops)
+    B = 2053
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, 8, B).astype(np.int32)
+    U = rand_batch(B, 16, 14)
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, 16)
+    didx = ctx.upload_array(idx)
+    _, E, Esum = table.mul_(du, u, 2.0, 0.0, op_index=didx.ptr, energy=True, energy_sum=True)
+    ref = np.stack([ops_o[idx[b]].mul(U[b], 2.0) for b in range(B)])
+    eref = np.array([ops_o[idx[b]].integrate(np.square, U[b]) for b in range(B)])
+    assert rel_err(du.to_host(), ref) <= TOL
+    assert np.max(np.abs(E - eref) / eref) <= TOL and abs(Esum - eref.sum()) <= TOL * eref.sum()
+
+
+@pytest.mark.parametrize("coupling", ["no", "central", "plus", "minus"])
+def test_subcell_single_operator_known_answers(ctx, coupling):
+    """test/test_subcell_operators.jl:127-255 on the device: exactness atol 1e-12, integrate == sum(M*f(u))."""
+    x_L, x_M, x_R = -2.3, -1.0, 0.4
+    Dop = S.couple_subcell(S.legendre_derivative_operator(x_L, x_M, 3), S.legendre_derivative_operator(x_M, x_R, 3),
+                           x_M, coupling)
+    x = Dop.grid
+    F = np.stack([np.ones_like(x), x, 0.5 * x**2])
+    dF = np.stack([np.zeros_like(x), np.ones_like(x), x])
+    assert np.max(np.abs((Dop * ctx.upload(F)).to_host() - dF)) <= 1e-12
+    u = np.sin(x)
+    d = ctx.upload(u)
+    assert abs(S.integrate(S.abs2, d, Dop) - np.sum(Dop.weights() * u * u)) < 1e-14
+    S.scale_by_mass_matrix_(d, Dop)
+    assert np.allclose(d.to_host()[0], Dop.mass_matrix() @ u, rtol=1e-15)
+    with pytest.raises(S.DimensionMismatch):
+        S.scale_by_mass_matrix_(ctx.upload(u[1:-1]), Dop)
+
+
+# ---- K5 reductions -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [5, 16, 64, 101, 1296])
+def test_integrate_modes(ctx, N):
+    w = np.random.default_rng(N).uniform(0.1, 1.0, N)
+    D = S.MatrixDerivativeOperator(0.0, 1.0, np.linspace(0, 1, N), w, np.zeros((N, N)) + np.eye(N), storage="dense")
+    B = 777
+    U, V = rand_batch(B, N, 1), rand_batch(B, N, 2)
+    u, v = ctx.upload(U), ctx.upload(V)
+    m0, t0 = S.integrate(S.identity, u, D, total=True)
+    m1 = S.integrate(S.abs2, u, D)
+    m2 = S.integrate(None, u, D, v=v)
+    assert np.max(np.abs(m0 - U @ w)) <= 1e-13 * N
+    assert np.max(np.abs(m1 - (U**2) @ w) / ((U**2) @ w)) <= TOL
+    assert np.max(np.abs(m2 - (U * V) @ w)) <= 1e-13 * N
+    assert abs(t0 - (U @ w).sum()) <= 1e-12 * np.abs(U @ w).sum()
+
+
+# ---- host-buffer (end-to-end) path -------------------------------------------------------------------------------
+def test_apply_host_pipeline(ctx):
+    import ctypes as C
+
+    N, B = 64, 70001
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, N)
+    Do = O.PolynomialBasesOperator("LobattoLegendre", -1.0, 1.0, N)
+    hU, hY = ctx.pinned_empty((B, N)), ctx.pinned_empty((B, N))
+    hU[:] = rand_batch(B, N, 4)
+    hY[:] = np.nan
+    op = D.device_op(ctx)
+    S._lib.check(ctx._lib.sbp_apply_host(ctx.handle, op.handle, hY.ctypes.data_as(C.c_void_p),
+                                         hU.ctypes.data_as(C.c_void_p), B, 1.0, 0.0, 8192))
+    assert rel_err(hY, O.apply_batch(Do.matrix(), hU)) <= TOL
+    Y0 = rand_batch(B, N, 5)
+    hY[:] = Y0
+    S._lib.check(ctx._lib.sbp_apply_host(ctx.handle, op.handle, hY.ctypes.data_as(C.c_void_p),
+                                         hU.ctypes.data_as(C.c_void_p), B, 2.0, -1.0, 0))
+    assert rel_err(hY, O.apply_batch(Do.matrix(), hU, 2.0, -1.0, Y0)) <= TOL
+    ctx.free_pinned(hU), ctx.free_pinned(hY)
+
+
+# ---- full-size configurations through size-independent properties ---------------------------------------------------
+def test_config2_full_size_properties(ctx):
+    """BASELINE config 2 at full size (N = 64, B = 2^20): instances are tiled copies of 2048 distinct vectors, so the
+    result must be the same tiling BITWISE (every instance sees the same arithmetic), the first block must match the
+    oracle, and the operator must be linear across the batch."""
+    N, B, R = 64, 1 << 20, 2048
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, N)
+    Do = O.PolynomialBasesOperator("LobattoLegendre", -1.0, 1.0, N)
+    base = rand_batch(R, N, 0)
+    u = ctx.upload(np.tile(base, (B // R, 1)))
+    du = D * u
+    out = du.to_host().reshape(B // R, R, N)
+    assert rel_err(out[0], O.apply_batch(Do.matrix(), base)) <= TOL
+    assert all(np.array_equal(out[0], out[k]) for k in range(1, B // R))
+    e, etot = S.integrate(S.abs2, u, D, total=True)
+    eref = O.energy_batch(Do.weights(), base)
+    assert np.max(np.abs(e[:R] - eref) / eref) <= TOL and abs(etot - eref.sum() * (B // R)) <= 1e-12 * etot
+
+
+def test_config5_sized_dense_gemm_checksum(ctx):
+    """config 5 shape at reduced batch (N = 4096 dense, B = 2048): column-checksum identity
+    sum_i w_i (D u)_i = (D' w)' u  for every instance."""
+    N, B = 4096, 2048
+    rng = np.random.default_rng(0)
+    Sk = rng.normal(size=(N, N))
+    Sk = Sk - Sk.T
+    w = rng.uniform(0.5, 1.5, N)
+    w *= 4.0 / w.sum()
+    Bd = np.zeros(N)
+    Bd[:256] = rng.normal(size=256)
+    Dm = (Sk + np.diag(Bd) / 2) / w[:, None]
+    D = S.MatrixDerivativeOperator(0.0, 1.0, np.linspace(0, 1, N), w, Dm, storage="dense")
+    U = rand_batch(B, N, 1)
+    u = ctx.upload(U)
+    du = D * u
+    lhs = S.integrate(S.identity, du, D)
+    rhs = U @ (Dm.T @ w)
+    scale = np.abs(U) @ (np.abs(Dm).T @ w)
+    assert np.max(np.abs(lhs - rhs) / scale) <= 1e-13
+    sub = du.to_host()[:64]
+    assert rel_err(sub, O.apply_batch(Dm, U[:64])) <= TOL

@@ -1,0 +1,206 @@
+"""CPU-only tests: host-side mirror vs the oracle, C-ABI symbol export, sharding logic, error behaviour.
+No compute call is made (there is no GPU here); the product must fail loudly instead of falling back."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sbp_b200 as S
+from oracle import sbp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ----------------------------------------------------------------------------------------
+def _header_functions():
+    txt = open(os.path.join(ROOT, "include", "sbp_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(sbp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = S.load()
+    names = _header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"libsbp_b200.so does not export {n}"
+    # and the ctypes table binds exactly the header's functions
+    assert sorted(S._lib.SIGNATURES) == names
+    assert lib.sbp_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(S.CudaError):
+        S.Context()
+    n = S._lib.c_i32()
+    assert S.load().sbp_device_count(n) == 0 and n.value == 0
+
+
+def test_error_codes_map_to_reference_exceptions():
+    assert issubclass(S.ArgumentError, ValueError) and issubclass(S.DimensionMismatch, ValueError)
+    lib = S.load()
+    # NULL ctx -> SBP_EINVAL -> ArgumentError, message retrievable
+    with pytest.raises(S.ArgumentError):
+        S._lib.check(lib.sbp_ctx_sync(None))
+    assert b"null" in lib.sbp_last_error()
+
+
+# ---- bases / operators vs oracle ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["LobattoLegendre", "GaussLegendre", "GaussRadauLeft", "GaussRadauRight"])
+@pytest.mark.parametrize("N", [2, 3, 5, 7, 16, 33])
+def test_bases_match_oracle(name, N):
+    if name == "LobattoLegendre" and N < 2:
+        pytest.skip()
+    b = getattr(S, name)(N - 1)
+    x, w = O.BASES[name](N)
+    assert np.allclose(b.nodes, x, rtol=0, atol=2e-15)
+    assert np.allclose(b.weights, w, rtol=0, atol=3e-15)
+    assert np.allclose(b.D, O.derivative_matrix_nodal(x), rtol=1e-12, atol=1e-12)
+
+
+def test_lgl64_host_operator():
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -1.0, 1.0, 64)
+    Do = O.PolynomialBasesOperator("LobattoLegendre", -1.0, 1.0, 64)
+    assert np.array_equal(D.grid, Do.grid)
+    assert np.max(np.abs(D.Matrix() - Do.matrix())) < 1e-10 * np.max(np.abs(Do.matrix()))
+    M, Dm, B = D.mass_matrix(), D.Matrix(), D.mass_matrix_boundary()
+    assert np.max(np.abs(M @ Dm + Dm.T @ M - B)) < 1e-12
+    assert D.accuracy_order == 63 and D.size() == (64, 64) and D.derivative_order == 1
+    assert D.get_weight(1) == D.left_boundary_weight and D.get_weight(64) == D.right_boundary_weight
+    with pytest.raises(S.ArgumentError):
+        D.get_weight(0)
+    with pytest.raises(S.ArgumentError):
+        S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, 0.0, 1.0, 1)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_mn2004_matches_oracle(order):
+    D, Do = S.mattsson_nordstrom_2004(order, -2.0, 4.0, 20), O.mattsson_nordstrom_2004(order, -2.0, 4.0, 20)
+    assert np.allclose(D.Matrix(), Do.matrix(), rtol=0, atol=1e-15)
+    assert np.allclose(D.weights(), Do.weights(), rtol=0, atol=1e-16)
+
+
+def test_tensor_product_and_corners_match_oracle():
+    D1, D1o = S.mattsson_nordstrom_2004(2, -1.0, 1.0, 4), O.mattsson_nordstrom_2004(2, -1.0, 1.0, 4)
+    D2, D2o = S.tensor_product_operator_2D(D1), O.tensor_product_operator_2D(D1o)
+    assert np.array_equal(D2.boundary_indices, D2o.boundary_indices)
+    assert np.array_equal(D2.normals, D2o.normals) and np.array_equal(D2.grid, D2o.nodes)
+    assert np.allclose(D2.Ds[0], D2o.Ds[0]) and np.allclose(D2.Ds[1], D2o.Ds[1])
+    assert S.find_corners(D2.boundary_indices) == O.find_corners(D2o.boundary_indices)
+    ex = O.tensor_product_corners(4, 4)
+    for dim in (0, 1):
+        assert np.array_equal(D2.mass_matrix_boundary_diag(dim), O.mass_matrix_boundary_2d(D2o, dim, ex))
+    # test/test_unit.jl:44-67: generic corner detection + swapped normals for the first two corners
+    cx, cy = S.find_corners(D2.boundary_indices)
+    ns = D2.normals.copy()
+    for k in (0, 1):
+        ns[[cx[k], cy[k]]] = ns[[cy[k], cx[k]]]
+    Dm = S.MultidimensionalMatrixDerivativeOperator(D2.grid, D2.boundary_indices, ns, D2.weights(), D2.weights_boundary,
+                                                    D2.Ds)
+    for dim in (0, 1):
+        assert np.array_equal(Dm.mass_matrix_boundary_diag(dim), D2.mass_matrix_boundary_diag(dim))
+
+
+@pytest.mark.parametrize("coupling", ["no", "central", "plus", "minus"])
+def test_couple_subcell_matches_oracle(coupling):
+    x_L, x_M, x_R = -2.3, -1.0, 0.4
+    a, b = S.legendre_derivative_operator(x_L, x_M, 5), S.legendre_derivative_operator(x_M, x_R, 4)
+    ao, bo = O.legendre_derivative_operator(x_L, x_M, 5), O.legendre_derivative_operator(x_M, x_R, 4)
+    Dop, Dopo = S.couple_subcell(a, b, x_M, coupling), O.couple_subcell(ao, bo, x_M, coupling)
+    assert np.allclose(Dop.Matrix(), Dopo.matrix(), rtol=1e-13, atol=1e-13)
+    assert np.allclose(Dop.weights(), Dopo.weights(), rtol=0, atol=1e-15)
+    assert np.allclose(Dop.B_left, Dopo.B_left, atol=1e-13) and np.allclose(Dop.B_right, Dopo.B_right, atol=1e-13)
+    assert Dop.get_weight(1) == Dop.left_boundary_weight and Dop.get_weight(Dop.N) == Dop.right_boundary_weight
+    assert Dop.get_weight_right(1) == 0.0 and Dop.get_weight_left(Dop.N) == 0.0
+    with pytest.raises(S.ArgumentError):
+        S.couple_subcell(a, b, -2.0)
+    with pytest.raises(S.ArgumentError):
+        S.couple_subcell(a, b, 0.0)
+    with pytest.raises(S.ArgumentError):
+        S.SubcellOperator(Dop.grid[:-1], x_M, Dop.weights_left, Dop.weights_right, Dop.Q_left, Dop.Q_right,
+                          Dop.B_left, Dop.B_right, Dop.e_L, Dop.e_M_L, Dop.e_M_R, Dop.e_R, 2)
+
+
+def test_sparsity_pattern_matches_oracle():
+    rng = np.random.default_rng(3)
+    nodes = rng.uniform(-1, 1, (40, 2))
+    assert np.array_equal(S.neighborhood_sparsity_pattern(nodes, (0.5, 0.3)),
+                          O.neighborhood_sparsity_pattern(nodes, (0.5, 0.3)))
+
+
+def test_advection2d_host_assembly_matches_oracle():
+    D1, D1o = S.mattsson_nordstrom_2004(2, -1.0, 1.0, 6), O.mattsson_nordstrom_2004(2, -1.0, 1.0, 6)
+    D2, D2o = S.tensor_product_operator_2D(D1), O.tensor_product_operator_2D(D1o)
+    a = (1.0, -0.5)
+    g = lambda x, t: np.sin(x[0] + 2 * x[1] - t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D2, a, g)
+    semio = O.AdvectionSemi2D(D2o, a, g, O.tensor_product_corners(6, 6))
+    assert np.allclose(semi.cache["A"], semio.A) and np.array_equal(semi.cache["B"], semio.B)
+    # mode + boundary values reproduce tmp1 of the sequential set_bc! loop for any u
+    u = np.random.default_rng(0).uniform(-1, 1, D2.N)
+    semio.set_bc(u, 0.7)
+    gv = semi.boundary_values(0.7)
+    tmp1 = np.where(semi.mode == 1, gv, np.where(semi.mode == 2, u, 0.0))
+    assert np.array_equal(tmp1, semio.tmp1)
+
+
+def test_analysis_callback_arguments():
+    D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, 4))
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D2, (1.0, 1.0), lambda x, t: 0.0)
+    cb = S.AnalysisCallback(semi, dt=0.1)
+    assert len(S.tstops(cb)) == 0 and len(S.quantities(cb)) == 0
+    cb = S.AnalysisCallback(semi, interval=10)
+    assert len(S.tstops(cb)) == 0
+    with pytest.raises(S.ArgumentError):  # test/test_unit.jl:105
+        S.AnalysisCallback(semi, interval=10, dt=0.1)
+    repr(cb), repr(semi)
+
+
+# ---- sharding (multi-GPU host logic) -------------------------------------------------------------------
+@pytest.mark.parametrize("B,ws,mult", [(1 << 20, 8, 1), (1000, 3, 8), (7, 8, 1), (0, 2, 1), (4194304, 4, 8)])
+def test_shard_range_partitions(B, ws, mult):
+    ranges = [S.shard_range(B, ws, r, mult) for r in range(ws)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == B
+    for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= mult
+    for a0, _ in ranges:
+        assert a0 % mult == 0 or a0 == B
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, N = 1003, 12
+    D = O.PolynomialBasesOperator("LobattoLegendre", -1.0, 1.0, N)
+    U = np.random.default_rng(0).uniform(-1, 1, (B, N))
+    b0, b1 = S.shard_range(B, world, rank)
+    local = O.energy_batch(D.weights(), U[b0:b1]).sum()  # stands in for the per-GPU energy_sum scalar
+    t = torch.tensor([local, float(b1 - b0)], dtype=torch.float64)
+    dist.all_reduce(t)  # the path's only collective: a sum of a few scalars
+    if rank == 0:
+        out.put((t[0].item(), t[1].item(), O.energy_batch(D.weights(), U).sum()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_energy_sum_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    total, count, ref = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert count == 1003
+    assert abs(total - ref) <= 1e-12 * abs(ref)
