@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -294,7 +294,10 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = S.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # run torch's allocator/RNG/events on the library's own (non-default) stream so that CUDA events bracket the
+    # kernels: torch's legacy default stream has handle 0, which sbp_ctx_set_stream treats as "use the ctx stream"
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    torch.cuda.set_stream(stream)
     lib, h = ctx._lib, ctx.handle
 
     N, B = N_NODES, BATCH  # per GPU (weak scaling)
@@ -430,8 +433,8 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3/4/5)")
     args = ap.parse_args()
