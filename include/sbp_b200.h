@@ -54,7 +54,12 @@ typedef struct sbp_op sbp_op;   /* immutable device-resident operator           
 /* flags for sbp_op_dense_create */
 #define SBP_DENSE_AUTO 0        /* pick kernel from N (smem-resident DMMA tiles or tiled DGEMM)  */
 #define SBP_DENSE_FORCE_GEMM 1  /* always use the tiled DGEMM path                                */
-#define SBP_DENSE_NO_SYMMETRY 2 /* do not exploit centro-(anti)symmetry even if D has it exactly  */
+#define SBP_DENSE_NO_SYMMETRY 2 /* do not exploit centro-antisymmetry even if D has it exactly     */
+/* By default the even/odd kernel is used only when D[N-1-i][N-1-j] == -D[i][j] holds BITWISE for all i, j
+ * (then it is the same operator, only the summation order differs).  With SBP_DENSE_SYMMETRIZE the antisymmetric
+ * part (D - J D J)/2 is used when |D + J D J|_max <= 256 eps |D|_max (operators that are centro-antisymmetric up to
+ * the rounding of their construction, e.g. a barycentric Legendre matrix); entries change by that amount. */
+#define SBP_DENSE_SYMMETRIZE 4
 
 /* ---- library / context ----------------------------------------------------------------- */
 int32_t sbp_version(void);

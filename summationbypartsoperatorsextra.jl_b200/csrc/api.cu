@@ -40,6 +40,9 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
                          double beta, const sbp_op* adv, const double* g, int64_t g_stride, const double* colscale);
 int32_t launch_adv1d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B,
                               const double* bc, int64_t bc_stride, double* quantities, bool apply_sat);
+static inline bool is_small(const sbp_op* op) {
+    return op->variant == SBP_KERNEL_DMMA_SMEM || op->variant == SBP_KERNEL_DMMA_SMEM_SYM;
+}
 __host__ __device__ inline int phys_k_host(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
 
 template <typename T>
@@ -106,6 +109,49 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
                 if (rc) return rc;
             }
             op->variant = SBP_KERNEL_DMMA_SMEM;
+            // ---- centro-antisymmetric operators: even/odd split, half the FP64 work (dense_small_sym.cu) ----
+            if (G == 1 && N % 16 == 0 && !(flags & SBP_DENSE_NO_SYMMETRY)) {
+                auto at = [&](int i, int k) { return h_D[(size_t)k * ldd + i]; };
+                double dev = 0.0, amax = 0.0;
+                for (int i = 0; i < N; i++)
+                    for (int k = 0; k < N; k++) {
+                        dev = std::max(dev, std::fabs(at(i, k) + at(N - 1 - i, N - 1 - k)));
+                        amax = std::max(amax, std::fabs(at(i, k)));
+                    }
+                const bool exact = dev == 0.0;
+                const bool approx = (flags & SBP_DENSE_SYMMETRIZE) && dev <= 256.0 * 2.220446049250313e-16 * amax;
+                if (exact || approx) {
+                    const int h = N / 2, NTH = N / 16, KSH = 2 * NTH;
+                    const size_t FH = (size_t)KSH * NTH * 32;
+                    std::vector<double> fs(2 * FH, 0.0);
+                    // antisymmetric part (== D when the symmetry is exact)
+                    auto da = [&](int i, int k) { return exact ? at(i, k) : 0.5 * (at(i, k) - at(N - 1 - i, N - 1 - k)); };
+                    for (int ks = 0; ks < KSH; ks++)
+                        for (int nt = 0; nt < NTH; nt++)
+                            for (int lane = 0; lane < 32; lane++) {
+                                const int i = nt * 8 + (lane >> 2), j = phys_k_host(ks, lane & 3);
+                                (void)h;
+                                const size_t o = ((size_t)ks * NTH + nt) * 32 + lane;
+                                fs[o] = 0.5 * (da(i, j) + da(i, N - 1 - j));       // E
+                                fs[FH + o] = 0.5 * (da(i, j) - da(i, N - 1 - j));  // O
+                            }
+                    rc = upload(&op->d_frag_sym, fs);
+                    if (rc) return rc;
+                    if (h_w) {
+                        std::vector<double> ws((size_t)2 * KSH * 4);
+                        for (int ks = 0; ks < KSH; ks++)
+                            for (int t = 0; t < 4; t++) {
+                                const int j = phys_k_host(ks, t);
+                                ws[ks * 4 + t] = h_w[j];
+                                ws[(size_t)KSH * 4 + ks * 4 + t] = h_w[N - 1 - j];
+                            }
+                        rc = upload(&op->d_wsym, ws);
+                        if (rc) return rc;
+                    }
+                    op->sym = true;
+                    op->variant = SBP_KERNEL_DMMA_SMEM_SYM;
+                }
+            }
         } else {
             op->variant = SBP_KERNEL_TABLE;  // table too large for shared memory: generic kernel only
         }
@@ -348,7 +394,7 @@ int32_t sbp_op_destroy(sbp_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     void* ptrs[] = {op->d_D,         op->d_frag,     op->d_wfrag,    op->d_w,        op->d_frag_sym, op->d_rowptr,
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
-                    op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts};
+                    op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -518,7 +564,7 @@ int32_t sbp_op_advection1d_create(sbp_ctx* ctx, const sbp_op* D, const double* h
         if (rc) goto fail;
     }
     if (!unit) {
-        if (D->kind == SBP_OP_DENSE && D->variant == SBP_KERNEL_DMMA_SMEM) {
+        if (D->kind == SBP_OP_DENSE && is_small(D)) {
             const int KS = 2 * D->NT;
             std::vector<double> cf((size_t)KS * 4, 0.0);
             for (int ks = 0; ks < KS; ks++)
@@ -557,6 +603,16 @@ int32_t sbp_op_info(const sbp_op* op, int32_t* kind, int32_t* N, int32_t* G, int
 }
 
 // ---- hot path -----------------------------------------------------------------------------------
+// tuning knob of the even/odd kernel (bit0 prefetch, bit1 one m-tile per warp, bit2 256-thread CTAs);
+// the default was picked from the sweep in profiles/ (tools/tune_sym.py)
+static int sym_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SBP_SYM_VARIANT");
+        v = e ? atoi(e) & 7 : 1;
+    }
+    return v;
+}
 static int32_t check_batch(sbp_ctx* ctx, const sbp_op* op, const void* dU, const void* U, int64_t B) {
     SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
     SBP_REQUIRE(op->ctx == ctx, SBP_EINVAL, "operator belongs to a different context");
@@ -575,12 +631,11 @@ int32_t sbp_apply(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, i
     SBP_CUDA(cudaSetDevice(ctx->device));
     switch (op->kind) {
         case SBP_OP_DENSE:
-            if (op->variant == SBP_KERNEL_DMMA_SMEM)
-                return launch_dense_small(ctx, op, dU, U, B, alpha, beta, false, nullptr, nullptr);
+            if (op->sym) return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, sym_variant());
+            if (is_small(op)) return launch_dense_small(ctx, op, dU, U, B, alpha, beta, false, nullptr, nullptr);
             return launch_dense_gemm(ctx, op, dU, U, B, alpha, beta);
         case SBP_OP_TABLE:
-            if (op->variant == SBP_KERNEL_DMMA_SMEM)
-                return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, nullptr, nullptr);
+            if (is_small(op)) return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, nullptr, nullptr);
             return launch_table_generic(ctx, op, dU, U, B, nullptr, alpha, beta, nullptr, nullptr);
         case SBP_OP_SPARSE:
             return launch_sparse(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, 0, nullptr);
@@ -607,7 +662,9 @@ int32_t sbp_apply_table(sbp_ctx* ctx, const sbp_op* op, double* dU, const double
         SBP_REQUIRE(op->d_w, SBP_EINVAL, "energy requested but the operator has no weights");
         return launch_integrate(ctx, op->d_w, op->N, 1, U, nullptr, B, 1, energy, energy_sum);
     }
-    if (op_index == nullptr && op->variant == SBP_KERNEL_DMMA_SMEM)
+    if (op_index == nullptr && op->sym)
+        return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, sym_variant());
+    if (op_index == nullptr && is_small(op))
         return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, energy, energy_sum);
     return launch_table_generic(ctx, op, dU, U, B, op_index, alpha, beta, energy, energy_sum);
 }
@@ -664,7 +721,9 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     const sbp_op* D = op->inner;
     if (D->kind == SBP_OP_SPARSE)
         rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a);
-    else if (D->variant == SBP_KERNEL_DMMA_SMEM)
+    else if (D->sym && op->d_a == nullptr)
+        rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant());
+    else if (is_small(D))
         rc = launch_dense_small_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, op->d_a);
     else
         rc = launch_dense_gemm(ctx, D, dU, U, B, -1.0, 0.0);

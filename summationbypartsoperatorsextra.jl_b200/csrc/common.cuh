@@ -65,7 +65,8 @@ struct sbp_op {
     double* d_w = nullptr;     // G*N weights (or nullptr)
     int NT = 0;                // n-tiles of 8 rows (small path)
     bool sym = false;          // centro-antisymmetric (even/odd split available)
-    double* d_frag_sym = nullptr;
+    double* d_frag_sym = nullptr;  // [E | O] half-operator fragments (dense_small_sym.cu)
+    double* d_wsym = nullptr;      // weights [w(j) | w(N-1-j)] in fragment k order
     // sparse (SELL-32 slices)
     int* d_rowptr = nullptr;
     int* d_col = nullptr;
@@ -90,6 +91,8 @@ namespace sbp {
 // kernel-family launchers (each in its own .cu)
 int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                            double beta, bool periodic_table, double* energy, double* energy_sum);
+int32_t launch_dense_small_sym(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                               double beta, double* energy, double* energy_sum, int variant);
 int32_t launch_table_generic(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
                              const int32_t* op_index, double alpha, double beta, double* energy, double* energy_sum);
 int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,

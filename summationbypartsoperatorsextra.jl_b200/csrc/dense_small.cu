@@ -10,6 +10,9 @@
 //                                          staged once per CTA into shared memory with a TMA bulk copy
 //   C fragment: a lane ends up with 2 consecutive output nodes of one instance -> 128-bit stores.
 // The contraction order is free, so one 128-bit load (nodes 8kp+2t, 8kp+2t+1) feeds two k-steps.
+// A warp owns work items (tile of 8*MT slots, operator gi); the raw 128-bit loads of the NEXT item are issued
+// right after the current item's values are unpacked, so HBM latency hides behind the DMMA chain (PREFETCH).
+#include <algorithm>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -33,7 +36,29 @@ struct DenseSmallParams {
 // physical node index of logical (k-step ks, lane-in-group t)
 __host__ __device__ __forceinline__ int phys_k(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
 
-template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE>
+// raw A data of one work item: MT m-tiles x NT 128-bit chunks per lane
+template <int NT, int MT, bool FULL>
+__device__ __forceinline__ void load_item(double2 (&raw)[MT][NT], const double* __restrict__ U, long long tile, int gi,
+                                          int G, int g, int t, int N, long long B) {
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const long long inst = (tile * (8 * MT) + mt * 8 + g) * G + gi;
+        const bool valid = inst < B;
+        const double* up = U + inst * N + 2 * t;
+#pragma unroll
+        for (int kp = 0; kp < NT; kp++) {
+            if (FULL) {
+                raw[mt][kp] = valid ? ldg_stream2(up + 8 * kp) : make_double2(0.0, 0.0);
+            } else {
+                const int k0 = 8 * kp + 2 * t;
+                raw[mt][kp].x = (valid && k0 < N) ? ldg_stream1(up + 8 * kp) : 0.0;
+                raw[mt][kp].y = (valid && k0 + 1 < N) ? ldg_stream1(up + 8 * kp + 1) : 0.0;
+            }
+        }
+    }
+}
+
+template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE, bool PREFETCH>
 __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams p) {
     constexpr int KS = 2 * NT;
     constexpr int FRAG = KS * NT * 32;
@@ -75,100 +100,107 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
     const long long B = p.B;
     const long long slots = (B + G - 1) / G;  // instance b = slot*G + gi
     const long long ntiles = (slots + 8 * MT - 1) / (8 * MT);
+    const long long tstride = (long long)gridDim.x * WARPS;
     const double alpha = p.alpha, beta = p.beta;
     double e_acc = 0.0;
 
-    for (long long tile = (long long)blockIdx.x * WARPS + warp; tile < ntiles; tile += (long long)gridDim.x * WARPS) {
-        for (int gi = 0; gi < G; gi++) {
-            // ---- A fragments: 8*MT instances, all N nodes, straight from global memory ----
-            double a[MT][KS];
-            long long inst[MT];
+    long long tile = (long long)blockIdx.x * WARPS + warp;
+    int gi = 0;
+    double2 raw[MT][NT];
+    if (PREFETCH && tile < ntiles) load_item<NT, MT, FULL>(raw, p.U, tile, gi, G, g, t, N, B);
+
+    while (tile < ntiles) {
+        if (!PREFETCH) load_item<NT, MT, FULL>(raw, p.U, tile, gi, G, g, t, N, B);
+        // ---- A fragments: unpack (node 8kp+2t -> k-step 2kp, node 8kp+2t+1 -> k-step 2kp+1) ----
+        double a[MT][KS];
+        long long inst[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            inst[mt] = (tile * (8 * MT) + mt * 8 + g) * G + gi;
+#pragma unroll
+            for (int kp = 0; kp < NT; kp++) {
+                a[mt][2 * kp] = raw[mt][kp].x;
+                a[mt][2 * kp + 1] = raw[mt][kp].y;
+            }
+        }
+        const int cur_gi = gi;
+        // next work item of this warp; its loads fly while the tensor pipe works on the current one
+        long long ntile = tile;
+        int ngi = gi + 1;
+        if (ngi == G) {
+            ngi = 0;
+            ntile = tile + tstride;
+        }
+        if (PREFETCH && ntile < ntiles) load_item<NT, MT, FULL>(raw, p.U, ntile, ngi, G, g, t, N, B);
+
+        // ---- fused discrete energy  u' P u  (warp-shuffle reduction over the 4 lanes of a group) ----
+        if (ENERGY) {
+            const double* wf = s_wfrag + cur_gi * KS * 4;
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                const long long slot = tile * (8 * MT) + mt * 8 + g;
-                inst[mt] = slot * G + gi;
-                const bool valid = inst[mt] < B;
-                const double* up = p.U + inst[mt] * N + 2 * t;
+                double e = 0.0;
 #pragma unroll
-                for (int kp = 0; kp < NT; kp++) {
-                    if (FULL) {
-                        double2 v = valid ? ldg_stream2(up + 8 * kp) : make_double2(0.0, 0.0);
-                        a[mt][2 * kp] = v.x;
-                        a[mt][2 * kp + 1] = v.y;
-                    } else {
-                        const int k0 = 8 * kp + 2 * t;
-                        a[mt][2 * kp] = (valid && k0 < N) ? ldg_stream1(up + 8 * kp) : 0.0;
-                        a[mt][2 * kp + 1] = (valid && k0 + 1 < N) ? ldg_stream1(up + 8 * kp + 1) : 0.0;
-                    }
+                for (int ks = 0; ks < KS; ks++) e = fma(wf[ks * 4 + t] * a[mt][ks], a[mt][ks], e);
+                e += __shfl_xor_sync(0xffffffffu, e, 1);
+                e += __shfl_xor_sync(0xffffffffu, e, 2);
+                if (t == 0 && inst[mt] < B) {
+                    if (p.energy) p.energy[inst[mt]] = e;
+                    e_acc += e;
                 }
             }
-            // ---- fused discrete energy  u' P u  (warp-shuffle reduction over the 4 lanes of a group) ----
-            if (ENERGY) {
-                const double* wf = s_wfrag + gi * KS * 4;
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    double e = 0.0;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++) e = fma(wf[ks * 4 + t] * a[mt][ks], a[mt][ks], e);
-                    e += __shfl_xor_sync(0xffffffffu, e, 1);
-                    e += __shfl_xor_sync(0xffffffffu, e, 2);
-                    if (t == 0 && inst[mt] < B) {
-                        if (p.energy) p.energy[inst[mt]] = e;
-                        e_acc += e;
-                    }
-                }
-            }
-            if (CSCALE) {
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-                    for (int ks = 0; ks < KS; ks++) a[mt][ks] *= s_cfrag[ks * 4 + t];
-            }
-            // ---- DMMA: C[mt][nt] += A[mt][ks] * Bfrag[ks][nt] ----
-            double c[MT][NT][2];
+        }
+        if (CSCALE) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) c[mt][nt][0] = c[mt][nt][1] = 0.0;
-            const double* bf = s_frag + (size_t)gi * FRAG + lane;
+                for (int ks = 0; ks < KS; ks++) a[mt][ks] *= s_cfrag[ks * 4 + t];
+        }
+        // ---- DMMA: C[mt][nt] += A[mt][ks] * Bfrag[ks][nt] ----
+        double c[MT][NT][2];
 #pragma unroll
-            for (int ks = 0; ks < KS; ks++) {
+        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    const double b = bf[(ks * NT + nt) * 32];
+            for (int nt = 0; nt < NT; nt++) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+        const double* bf = s_frag + (size_t)cur_gi * FRAG + lane;
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt][ks], b);
-                }
+        for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+                const double b = bf[(ks * NT + nt) * 32];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt][ks], b);
             }
-            // ---- epilogue: lane owns nodes (8nt+2t, 8nt+2t+1) of instance g of each m-tile ----
+        }
+        // ---- epilogue: lane owns nodes (8nt+2t, 8nt+2t+1) of instance g of each m-tile ----
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                if (inst[mt] >= B) continue;
-                double* yp = p.dU + inst[mt] * N + 2 * t;
+        for (int mt = 0; mt < MT; mt++) {
+            if (inst[mt] >= B) continue;
+            double* yp = p.dU + inst[mt] * N + 2 * t;
 #pragma unroll
-                for (int nt = 0; nt < NT; nt++) {
-                    double y0 = alpha * c[mt][nt][0], y1 = alpha * c[mt][nt][1];
-                    if (FULL) {
-                        if (beta != 0.0) {
-                            const double2 o = *reinterpret_cast<const double2*>(yp + 8 * nt);
-                            y0 = fma(beta, o.x, y0);
-                            y1 = fma(beta, o.y, y1);
-                        }
-                        stg_stream2(yp + 8 * nt, y0, y1);
-                    } else {
-                        const int r0 = 8 * nt + 2 * t;
-                        if (r0 < N) {
-                            if (beta != 0.0) y0 = fma(beta, yp[8 * nt], y0);
-                            stg_stream1(yp + 8 * nt, y0);
-                        }
-                        if (r0 + 1 < N) {
-                            if (beta != 0.0) y1 = fma(beta, yp[8 * nt + 1], y1);
-                            stg_stream1(yp + 8 * nt + 1, y1);
-                        }
+            for (int nt = 0; nt < NT; nt++) {
+                double y0 = alpha * c[mt][nt][0], y1 = alpha * c[mt][nt][1];
+                if (FULL) {
+                    if (beta != 0.0) {
+                        const double2 o = *reinterpret_cast<const double2*>(yp + 8 * nt);
+                        y0 = fma(beta, o.x, y0);
+                        y1 = fma(beta, o.y, y1);
+                    }
+                    stg_stream2(yp + 8 * nt, y0, y1);
+                } else {
+                    const int r0 = 8 * nt + 2 * t;
+                    if (r0 < N) {
+                        if (beta != 0.0) y0 = fma(beta, yp[8 * nt], y0);
+                        stg_stream1(yp + 8 * nt, y0);
+                    }
+                    if (r0 + 1 < N) {
+                        if (beta != 0.0) y1 = fma(beta, yp[8 * nt + 1], y1);
+                        stg_stream1(yp + 8 * nt + 1, y1);
                     }
                 }
             }
         }
+        tile = ntile;
+        gi = ngi;
     }
     if (ENERGY && p.partial) {
         e_acc = warp_sum(e_acc);
@@ -182,10 +214,10 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
     }
 }
 
-template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE>
+template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE, bool PREFETCH>
 static int32_t launch_variant(sbp_ctx* ctx, const DenseSmallParams& p, double* energy_sum) {
     constexpr int KS = 2 * NT;
-    auto kern = k_dense_small<NT, MT, THREADS, FULL, ENERGY, CSCALE>;
+    auto kern = k_dense_small<NT, MT, THREADS, FULL, ENERGY, CSCALE, PREFETCH>;
     size_t smem = (size_t)p.G * KS * NT * 32 * 8 + (ENERGY ? (size_t)p.G * KS * 4 * 8 : 0) + (CSCALE ? KS * 4 * 8 : 0);
     SBP_REQUIRE((int64_t)smem <= ctx->smem_optin - 1024, SBP_EUNSUPPORTED,
                 "operator table needs %zu bytes of shared memory (> %lld available)", smem,
@@ -213,11 +245,14 @@ static int32_t launch_variant(sbp_ctx* ctx, const DenseSmallParams& p, double* e
 
 template <int NT>
 static int32_t dispatch_nt(sbp_ctx* ctx, const DenseSmallParams& p, bool full, bool energy, bool cscale,
-                           double* energy_sum) {
+                           double* energy_sum, int variant) {
     // m-tiles per warp iteration: keep ~64 accumulator doubles per lane at most
     constexpr int MT = (NT <= 2) ? 4 : (NT <= 8 ? 2 : 1);
     constexpr int TH = 128;
-#define SBP_DS(F, E, C) return launch_variant<NT, MT, TH, F, E, C>(ctx, p, energy_sum)
+    // variant bit0: software prefetch of the next work item (tuning knob SBP_DS_VARIANT, default on)
+#define SBP_DS(F, E, C)                                                                 \
+    return (variant & 1) ? launch_variant<NT, MT, TH, F, E, C, true>(ctx, p, energy_sum) \
+                         : launch_variant<NT, MT, TH, F, E, C, false>(ctx, p, energy_sum)
     if (full) {
         if (energy) {
             if (cscale) SBP_DS(true, true, true);
@@ -233,6 +268,15 @@ static int32_t dispatch_nt(sbp_ctx* ctx, const DenseSmallParams& p, bool full, b
     if (cscale) SBP_DS(false, false, true);
     SBP_DS(false, false, false);
 #undef SBP_DS
+}
+
+static int ds_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SBP_DS_VARIANT");
+        v = e ? atoi(e) & 1 : 1;
+    }
+    return v;
 }
 
 int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
@@ -255,10 +299,11 @@ int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const 
     const bool full = (op->N == op->NT * 8) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
     const bool cs = cfrag != nullptr;
+    const int variant = ds_variant();
     switch (op->NT) {
 #define SBP_CASE(n) \
     case n:         \
-        return dispatch_nt<n>(ctx, p, full, want_energy, cs, energy_sum);
+        return dispatch_nt<n>(ctx, p, full, want_energy, cs, energy_sum, variant);
         SBP_CASE(1)
         SBP_CASE(2)
         SBP_CASE(3)

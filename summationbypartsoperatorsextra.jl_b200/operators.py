@@ -142,6 +142,9 @@ class DerivativeOperator:
     `_scale()` (constant folded into every apply), `weights()` and `grid`."""
 
     storage = "auto"  # "auto" | "dense" | "sparse"
+    # sbp_op_dense_create flags: 0 = use the even/odd kernel iff D is bitwise centro-antisymmetric;
+    # _lib.DENSE_NO_SYMMETRY never; _lib.DENSE_SYMMETRIZE also when it is so up to 256 eps (uses (D - JDJ)/2)
+    dense_flags = _lib.DENSE_AUTO
 
     def __init__(self):
         self._dev: dict[int, _DeviceOp] = {}
@@ -193,7 +196,7 @@ class DerivativeOperator:
             if self._want_sparse(D):
                 op = upload_sparse(ctx, D, self.weights(), self._scale())
             else:
-                op = upload_dense(ctx, D, self.weights(), self._scale())
+                op = upload_dense(ctx, D, self.weights(), self._scale(), self.dense_flags)
             self._dev[key] = op
         return op
 
@@ -306,6 +309,10 @@ class NodalBasis:
         D = (lam[None, :] / lam[:, None]) / diff
         np.fill_diagonal(D, 0.0)
         np.fill_diagonal(D, -D.sum(axis=1))
+        if np.array_equal(x, -x[::-1]):
+            # node set symmetric about 0 => the exact derivative matrix is centro-antisymmetric; impose it exactly
+            # (removes the O(eps) asymmetry of the barycentric products and lets the device use the even/odd kernel)
+            D = 0.5 * (D - D[::-1, ::-1])
         self.D = D
 
     def interpolation_matrix(self, dest) -> np.ndarray:
