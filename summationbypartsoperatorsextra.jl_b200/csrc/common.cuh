@@ -72,6 +72,7 @@ struct sbp_op {
     int* d_col = nullptr;
     double* d_val = nullptr;
     int n_slices = 0;
+    int logR = 0;                // rows per lane = 1 << logR (row-blocked SELL, sparse.cu)
     int* d_slice_ptr = nullptr;  // n_slices+1 offsets (in units of 32-wide columns)
     int* d_sell_col = nullptr;
     double* d_sell_val = nullptr;

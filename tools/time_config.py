@@ -59,6 +59,44 @@ def main():
         def step(i):
             S._lib.check(lib.sbp_apply_table(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, None,
                                              1.0, 0.0, C.c_void_p(E.data_ptr()), C.c_void_p(E.data_ptr() + 8 * B)))
+    elif args.workload in ("config3", "config1b"):
+        if args.workload == "config3":  # 2D MFSBP advection RHS with SAT on a jittered 36x36 cloud
+            n1, B = 36, 65536
+            rng = np.random.default_rng(0)
+            D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, n1))
+            nodes = D2.grid.copy()
+            interior = np.ones(D2.N, bool)
+            interior[np.unique(D2.boundary_indices)] = False
+            if not os.environ.get("SBP_BENCH_REGULAR"):  # regular grid => identical stencil offsets on every row
+                nodes[interior] += (2.0 / (n1 - 1)) / 6 * (1 - 2 * rng.uniform(size=(int(interior.sum()), 2)))
+            Ds = []
+            for dim, lengths in ((0, (0.14, 0.08)), (1, (0.08, 0.14))):
+                pat = S.neighborhood_sparsity_pattern(nodes, lengths)
+                pat = pat | pat.T | np.eye(D2.N, dtype=bool)
+                Dd = D2.Ds[dim].copy()
+                extra = pat & (Dd == 0)
+                Dd[extra] = 0.05 * rng.normal(size=int(extra.sum()))
+                Ds.append(Dd)
+            Dm = S.MultidimensionalMatrixDerivativeOperator(nodes, D2.boundary_indices, D2.normals, D2.weights(),
+                                                            D2.weights_boundary, Ds, 2, corners=D2.corners)
+            semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(
+                Dm, (1.0, 1.0), lambda x, t: float(np.exp(-30 * ((x[0] - t) ** 2 + (x[1] - t) ** 2))),
+                storage="sparse")
+            N = Dm.N
+        else:  # config 1 batched: banded 1D operator N = 101, SAT at both ends
+            N, B = 101, 1 << 19
+            D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+            D1.storage = "sparse"
+            semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False,
+                                                                          lambda t: 0.3, lambda t: 0.0)
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+        u, du = S.DeviceBatch.from_torch(ctx, U), S.DeviceBatch.from_torch(ctx, Y)
+        semi(du, u, None, 0.1)
+        op = semi.device_op(ctx)
+
+        def step(i):
+            semi(du, u, None, 0.1)
     else:
         raise SystemExit("unknown workload")
     for i in range(5):
