@@ -109,6 +109,30 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
                 if (rc) return rc;
             }
             op->variant = SBP_KERNEL_DMMA_SMEM;
+            // ---- "layout 4" image for the 256-bit kernel (dense_small_v4.cu): permuted k and output-row orders ----
+            if (N % 16 == 0) {
+                auto kap = [](int ks, int t) { return 16 * (ks >> 2) + 4 * t + (ks & 3); };
+                auto rho = [](int nt, int n) { return 16 * (nt >> 1) + 4 * (n >> 1) + 2 * (nt & 1) + (n & 1); };
+                std::vector<double> f4(G * FR, 0.0);
+                for (int g = 0; g < G; g++) {
+                    const double* Dg = h_D + (size_t)g * ldd * N;
+                    for (int ks = 0; ks < KS; ks++)
+                        for (int nt = 0; nt < NT; nt++)
+                            for (int lane = 0; lane < 32; lane++)
+                                f4[g * FR + ((size_t)ks * NT + nt) * 32 + lane] =
+                                    Dg[(size_t)kap(ks, lane & 3) * ldd + rho(nt, lane >> 2)];
+                }
+                rc = upload(&op->d_frag4, f4);
+                if (rc) return rc;
+                if (h_w) {
+                    std::vector<double> w4((size_t)G * KS * 4);
+                    for (int g = 0; g < G; g++)
+                        for (int ks = 0; ks < KS; ks++)
+                            for (int t = 0; t < 4; t++) w4[(size_t)g * KS * 4 + ks * 4 + t] = h_w[(size_t)g * N + kap(ks, t)];
+                    rc = upload(&op->d_wfrag4, w4);
+                    if (rc) return rc;
+                }
+            }
             // ---- centro-antisymmetric operators: even/odd split, half the FP64 work (dense_small_sym.cu) ----
             if (G == 1 && N % 16 == 0 && !(flags & SBP_DENSE_NO_SYMMETRY)) {
                 auto at = [&](int i, int k) { return h_D[(size_t)k * ldd + i]; };
@@ -437,7 +461,8 @@ int32_t sbp_op_destroy(sbp_op* op) {
     cudaStreamSynchronize(op->ctx->stream);
     void* ptrs[] = {op->d_D,         op->d_frag,     op->d_wfrag,    op->d_w,        op->d_frag_sym, op->d_rowptr,
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
-                    op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym};
+                    op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
+                    op->d_frag4,     op->d_wfrag4};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;

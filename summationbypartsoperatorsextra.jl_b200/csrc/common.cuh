@@ -67,6 +67,8 @@ struct sbp_op {
     bool sym = false;          // centro-antisymmetric (even/odd split available)
     double* d_frag_sym = nullptr;  // [E | O] half-operator fragments (dense_small_sym.cu)
     double* d_wsym = nullptr;      // weights [w(j) | w(N-1-j)] in fragment k order
+    double* d_frag4 = nullptr;     // fragment image in "layout 4" (256-bit accesses, dense_small_v4.cu), N % 16 == 0
+    double* d_wfrag4 = nullptr;
     // sparse (SELL-32 slices)
     int* d_rowptr = nullptr;
     int* d_col = nullptr;
@@ -94,6 +96,8 @@ int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const dou
                            double beta, bool periodic_table, double* energy, double* energy_sum);
 int32_t launch_dense_small_sym(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                                double beta, double* energy, double* energy_sum, int variant);
+int32_t launch_dense_small_v4(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                              double beta, double* energy, double* energy_sum, int variant);
 int32_t launch_table_generic(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
                              const int32_t* op_index, double alpha, double beta, double* energy, double* energy_sum);
 int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,

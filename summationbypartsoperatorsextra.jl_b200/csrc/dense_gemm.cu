@@ -11,14 +11,6 @@
 
 namespace sbp {
 
-namespace gemm {
-constexpr int BM = 128, BN = 128, BK = 16, LD = BK + 4;  // LD % 16 == 4 -> conflict-free fragment loads
-constexpr int STAGES = 4, THREADS = 256;
-constexpr int WM = 64, WN = 32;                           // warp tile: 8 m-tiles x 4 n-tiles
-constexpr int MT = WM / 8, NTW = WN / 8;
-constexpr int STAGE_DOUBLES = (BM + BN) * LD;
-}  // namespace gemm
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes)
                  : "memory");
@@ -29,18 +21,32 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <bool VEC>
+// CTA tile BM x BN x BK, WGM x WGN warps, each warp (BM/WGM) x (BN/WGN); LD = BK + 4 keeps LD % 16 == 4, which makes the
+// 8-row x 4-column fragment loads (lane = 4*row + col) hit 32 distinct 8-byte banks.
+template <int BM_, int BN_, int BK_, int WGM_, int WGN_, int STAGES_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, BK = BK_, WGM = WGM_, WGN = WGN_, STAGES = STAGES_;
+    static constexpr int LD = BK + 4;
+    static constexpr int THREADS = WGM * WGN * 32;
+    static constexpr int WM = BM / WGM, WN = BN / WGN;
+    static constexpr int MT = WM / 8, NTW = WN / 8;
+    static constexpr int STAGE_DOUBLES = (BM + BN) * LD;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
+};
+
+template <class C, bool VEC, int ROWS>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ G, long long row0, long long rows,
                                           int k0, int K, int tid) {
-    using namespace gemm;
-    // 128 rows x 16 doubles -> 1024 16-byte chunks, 4 per thread
+    constexpr int CHUNKS_PER_ROW = C::BK / 2;  // 16-byte chunks
+    constexpr int TOTAL = ROWS * CHUNKS_PER_ROW;
 #pragma unroll
-    for (int it = 0; it < 4; it++) {
-        const int chunk = tid + it * THREADS;
-        const int r = chunk >> 3, c = (chunk & 7) * 2;
+    for (int it = 0; it < (TOTAL + C::THREADS - 1) / C::THREADS; it++) {
+        const int chunk = tid + it * C::THREADS;
+        if (TOTAL % C::THREADS != 0 && chunk >= TOTAL) break;
+        const int r = chunk / CHUNKS_PER_ROW, c = (chunk % CHUNKS_PER_ROW) * 2;
         const long long gr = row0 + r;
         const int gk = k0 + c;
-        double* dst = s + r * LD + c;
+        double* dst = s + r * C::LD + c;
         if (VEC) {
             int bytes = 0;
             if (gr < rows && gk < K) bytes = (K - gk >= 2) ? 16 : 8;
@@ -53,15 +59,15 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
     }
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(gemm::THREADS, 1)
+template <class C, bool VEC>
+__global__ void __launch_bounds__(C::THREADS, 1)
     k_dense_gemm(const double* __restrict__ U, const double* __restrict__ Drm, double* __restrict__ Y, long long B,
                  int N, double alpha, double beta, int tiles_n, long long tiles_total) {
-    using namespace gemm;
+    constexpr int BM = C::BM, BN = C::BN, BK = C::BK, LD = C::LD, STAGES = C::STAGES, MT = C::MT, NTW = C::NTW;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = (warp >> 2) * WM, wn = (warp & 3) * WN;
+    const int wm = (warp / C::WGN) * C::WM, wn = (warp % C::WGN) * C::WN;
     const int KT = (N + BK - 1) / BK;
 
     for (long long tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
@@ -81,9 +87,9 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
 #pragma unroll
         for (int s = 0; s < STAGES - 1; s++) {
             if (s < KT) {
-                double* sa = smem + s * STAGE_DOUBLES;
-                load_tile<VEC>(sa, U, m0, B, s * BK, N, tid);
-                load_tile<VEC>(sa + BM * LD, Drm, n0, N, s * BK, N, tid);
+                double* sa = smem + s * C::STAGE_DOUBLES;
+                load_tile<C, VEC, BM>(sa, U, m0, B, s * BK, N, tid);
+                load_tile<C, VEC, BN>(sa + BM * LD, Drm, n0, N, s * BK, N, tid);
             }
             cp_async_commit();
         }
@@ -93,13 +99,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
             {   // prefetch stage kt+STAGES-1 into the slot freed at iteration kt-1
                 const int kn = kt + STAGES - 1;
                 if (kn < KT) {
-                    double* sa = smem + (kn % STAGES) * STAGE_DOUBLES;
-                    load_tile<VEC>(sa, U, m0, B, kn * BK, N, tid);
-                    load_tile<VEC>(sa + BM * LD, Drm, n0, N, kn * BK, N, tid);
+                    double* sa = smem + (kn % STAGES) * C::STAGE_DOUBLES;
+                    load_tile<C, VEC, BM>(sa, U, m0, B, kn * BK, N, tid);
+                    load_tile<C, VEC, BN>(sa + BM * LD, Drm, n0, N, kn * BK, N, tid);
                 }
                 cp_async_commit();
             }
-            const double* sa = smem + (kt % STAGES) * STAGE_DOUBLES;
+            const double* sa = smem + (kt % STAGES) * C::STAGE_DOUBLES;
             const double* sb = sa + BM * LD;
 #pragma unroll
             for (int k4 = 0; k4 < BK / 4; k4++) {
@@ -116,7 +122,6 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
         }
         cp_async_wait<0>();
         // ---- epilogue ----
-        const bool vec_store = VEC;  // N even and base 16-byte aligned
 #pragma unroll
         for (int i = 0; i < MT; i++) {
             const long long m = m0 + wm + i * 8 + g;
@@ -126,7 +131,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
                 const int n = n0 + wn + j * 8 + 2 * t;
                 double y0 = alpha * c[i][j][0], y1 = alpha * c[i][j][1];
                 double* yp = Y + m * N + n;
-                if (vec_store && n + 1 < N) {
+                if (VEC && n + 1 < N) {
                     if (beta != 0.0) {
                         const double2 o = *reinterpret_cast<const double2*>(yp);
                         y0 = fma(beta, o.x, y0);
@@ -142,29 +147,46 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
     }
 }
 
-int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+template <class C>
+static int32_t launch_cfg(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                           double beta) {
-    using namespace gemm;
     const int N = op->N;
-    const int tiles_n = (N + BN - 1) / BN;
-    const long long tiles_m = (B + BM - 1) / BM;
+    const int tiles_n = (N + C::BN - 1) / C::BN;
+    const long long tiles_m = (B + C::BM - 1) / C::BM;
     const long long total = tiles_m * tiles_n;
-    const size_t smem = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);
     const bool vec = (N % 2 == 0) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
-    int grid = (int)std::max<long long>(1, std::min<long long>(total, ctx->sm_count));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(total, ctx->sm_count));
     if (vec) {
-        SBP_CUDA(cudaFuncSetAttribute(k_dense_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dense_gemm<true><<<grid, THREADS, smem, ctx->stream>>>(U, op->d_D, dU, B, N, alpha * op->scale, beta,
-                                                                  tiles_n, total);
+        SBP_CUDA(cudaFuncSetAttribute(k_dense_gemm<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        k_dense_gemm<C, true><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(U, op->d_D, dU, B, N, alpha * op->scale, beta,
+                                                                          tiles_n, total);
     } else {
-        SBP_CUDA(cudaFuncSetAttribute(k_dense_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dense_gemm<false><<<grid, THREADS, smem, ctx->stream>>>(U, op->d_D, dU, B, N, alpha * op->scale, beta,
-                                                                   tiles_n, total);
+        SBP_CUDA(cudaFuncSetAttribute(k_dense_gemm<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        k_dense_gemm<C, false><<<grid, C::THREADS, C::SMEM, ctx->stream>>>(U, op->d_D, dU, B, N, alpha * op->scale,
+                                                                           beta, tiles_n, total);
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
+}
+
+int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                          double beta) {
+    // tuning knob SBP_GEMM_VARIANT (tools/time_config.py --workload config5 sweeps it)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SBP_GEMM_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    switch (v) {
+        case 1: return launch_cfg<GemmCfg<128, 128, 16, 4, 4, 4>>(ctx, op, dU, U, B, alpha, beta);  // 16 warps, 32x32
+        case 2: return launch_cfg<GemmCfg<128, 128, 32, 2, 4, 3>>(ctx, op, dU, U, B, alpha, beta);  // BK = 32
+        case 3: return launch_cfg<GemmCfg<128, 128, 32, 4, 4, 3>>(ctx, op, dU, U, B, alpha, beta);
+        case 4: return launch_cfg<GemmCfg<128, 128, 16, 2, 4, 3>>(ctx, op, dU, U, B, alpha, beta);  // 3 stages
+        case 5: return launch_cfg<GemmCfg<128, 128, 16, 4, 2, 4>>(ctx, op, dU, U, B, alpha, beta);  // 32x64 warp tiles
+        default: return launch_cfg<GemmCfg<128, 128, 16, 2, 4, 4>>(ctx, op, dU, U, B, alpha, beta);  // 8 warps, 64x32
+    }
 }
 
 }  // namespace sbp

@@ -296,6 +296,16 @@ int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const 
     p.partial = nullptr;
     const bool want_energy = (energy != nullptr) || (energy_sum != nullptr);
     SBP_REQUIRE(!want_energy || op->d_wfrag, SBP_EINVAL, "energy requested but the operator has no weights");
+    // 256-bit variant (N % 16 == 0, 32-byte aligned batches, no column scaling); SBP_DS_V4 = -1 disables it,
+    // otherwise its low bits select the variant (bit0 prefetch, bit1 fewer m-tiles per item)
+    static int v4 = -2;
+    if (v4 == -2) {
+        const char* e = getenv("SBP_DS_V4");
+        v4 = e ? atoi(e) : 1;
+    }
+    if (v4 >= 0 && op->d_frag4 && cfrag == nullptr && ((reinterpret_cast<uintptr_t>(U) & 31) == 0) &&
+        ((reinterpret_cast<uintptr_t>(dU) & 31) == 0))
+        return launch_dense_small_v4(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, v4);
     const bool full = (op->N == op->NT * 8) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
     const bool cs = cfrag != nullptr;

@@ -125,6 +125,21 @@ __device__ __forceinline__ void stg_stream1(double* p, double x) {
     asm volatile("st.global.cs.f64 [%0], %1;\n" ::"l"(p), "d"(x) : "memory");
 }
 
+// 256-bit accesses (sm_100+: SASS LDG.E.256 / STG.E.256): one lane moves a whole 32-byte sector
+struct double4v {
+    double x, y, z, w;
+};
+__device__ __forceinline__ double4v ldg_stream4(const double* p) {
+    double4v v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\n"
+                 : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream4(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -59,6 +59,16 @@ def main():
         def step(i):
             S._lib.check(lib.sbp_apply_table(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, None,
                                              1.0, 0.0, C.c_void_p(E.data_ptr()), C.c_void_p(E.data_ptr() + 8 * B)))
+    elif args.workload == "config5":
+        N, B = 4096, 1 << (args.batch_log2 if args.batch_log2 != 20 else 13)
+        rng = np.random.default_rng(0)
+        Sk = rng.normal(size=(N, N))
+        op = S.upload_dense(ctx, Sk - Sk.T, np.ones(N))
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+
+        def step(i):
+            S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
     elif args.workload in ("config3", "config1b"):
         if args.workload == "config3":  # 2D MFSBP advection RHS with SAT on a jittered 36x36 cloud
             n1, B = 36, 65536
