@@ -60,6 +60,10 @@ typedef struct sbp_op sbp_op;   /* immutable device-resident operator           
  * part (D - J D J)/2 is used when |D + J D J|_max <= 256 eps |D|_max (operators that are centro-antisymmetric up to
  * the rounding of their construction, e.g. a barycentric Legendre matrix); entries change by that amount. */
 #define SBP_DENSE_SYMMETRIZE 4
+/* Small dense operators whose (4-column x 8-row) fragments are >= 25% structurally zero (banded FSBP / FD-SBP
+ * operators stored dense, block-diagonal sub-cell operators) skip those fragments; exact for finite inputs
+ * (0*x == 0), differs for Inf/NaN inputs exactly like the sparse path.  This flag multiplies the stored zeros. */
+#define SBP_DENSE_NO_SKIP 8
 
 /* ---- library / context ----------------------------------------------------------------- */
 int32_t sbp_version(void);

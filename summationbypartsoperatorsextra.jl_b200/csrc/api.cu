@@ -35,15 +35,20 @@ int32_t ensure_scratch(sbp_ctx* ctx, size_t doubles) {
 }
 
 int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
-                              double beta, double* energy, double* energy_sum, const double* cfrag);
+                              double beta, double* energy, double* energy_sum, const double* cfrag,
+                              const Sat1D* sat);
 int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
-                         double beta, const sbp_op* adv, const double* g, int64_t g_stride, const double* colscale);
+                         double beta, const sbp_op* adv, const double* g, int64_t g_stride, const double* colscale,
+                         const Sat1D* sat);
 int32_t launch_adv1d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B,
                               const double* bc, int64_t bc_stride, double* quantities, bool apply_sat);
 static inline bool is_small(const sbp_op* op) {
     return op->variant == SBP_KERNEL_DMMA_SMEM || op->variant == SBP_KERNEL_DMMA_SMEM_SYM;
 }
 __host__ __device__ inline int phys_k_host(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
+// fragment layouts of dense_small.cu: node of (k-step, lane-in-group) and output row of (n-tile, column)
+static inline int frag_k(int layout, int ks, int t) { return layout == 2 ? phys_k_host(ks, t) : 4 * ks + t; }
+static inline int frag_row(int layout, int nt, int n) { return layout == 2 ? 8 * nt + n : 8 * nt + (n >> 1) + 4 * (n & 1); }
 
 template <typename T>
 static int32_t upload(T** dptr, const std::vector<T>& h) {
@@ -84,16 +89,31 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
         op->NT = NT;
         const size_t FR = (size_t)KS * NT * 32;
         if ((int64_t)(G * FR * 8 + G * KS * 32 + 4096) <= ctx->smem_optin) {
+            // fragment layout (dense_small.cu): 2 = paired k order / natural rows (N % 8 == 0, 128-bit accesses),
+            //                                   1 = natural k order / interleaved rows (any N, 64-bit accesses)
+            op->layout = (N % 8 == 0) ? 2 : 1;
+            const int layout = op->layout;
             std::vector<double> frag(G * FR, 0.0), wfrag;
+            size_t nonzero_blocks = 0;
+            int band = 0;  // max |k-pair - n-tile| over the non-zero fragments
             for (int g = 0; g < G; g++) {
                 const double* Dg = h_D + (size_t)g * ldd * N;
                 for (int ks = 0; ks < KS; ks++)
-                    for (int nt = 0; nt < NT; nt++)
+                    for (int nt = 0; nt < NT; nt++) {
+                        bool any = false;
                         for (int lane = 0; lane < 32; lane++) {
-                            const int row = nt * 8 + (lane >> 2), col = phys_k_host(ks, lane & 3);
-                            if (row < N && col < N)
-                                frag[g * FR + ((size_t)ks * NT + nt) * 32 + lane] = Dg[(size_t)col * ldd + row];
+                            const int row = frag_row(layout, nt, lane >> 2), col = frag_k(layout, ks, lane & 3);
+                            if (row < N && col < N) {
+                                const double v = Dg[(size_t)col * ldd + row];
+                                frag[g * FR + ((size_t)ks * NT + nt) * 32 + lane] = v;
+                                any = any || (v != 0.0);
+                            }
                         }
+                        if (any) {
+                            band = std::max(band, std::abs((ks >> 1) - nt));
+                            nonzero_blocks++;
+                        }
+                    }
             }
             rc = upload(&op->d_frag, frag);
             if (rc) return rc;
@@ -102,12 +122,19 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
                 for (int g = 0; g < G; g++)
                     for (int ks = 0; ks < KS; ks++)
                         for (int t = 0; t < 4; t++) {
-                            const int k = phys_k_host(ks, t);
+                            const int k = frag_k(layout, ks, t);
                             if (k < N) wfrag[(size_t)g * KS * 4 + ks * 4 + t] = h_w[(size_t)g * N + k];
                         }
                 rc = upload(&op->d_wfrag, wfrag);
                 if (rc) return rc;
             }
+            // banded operators: fragments with |k-pair - n-tile| > band are structurally zero and are not multiplied
+            const double zero_frac = 1.0 - (double)nonzero_blocks / ((double)G * KS * NT);
+            op->zero_frac = zero_frac;
+            const double kept = std::min(1.0, (2.0 * band + 1.0) / NT);  // fraction of fragments inside the band
+            if (band >= 1 && band <= 2 && kept <= 0.75 && NT >= (band == 1 ? 4 : 6) && !(flags & SBP_DENSE_NO_SKIP))
+                op->band = band;
+            if (band == 0 && NT >= 4 && !(flags & SBP_DENSE_NO_SKIP)) op->band = 1;  // block diagonal: use band 1
             op->variant = SBP_KERNEL_DMMA_SMEM;
             // ---- "layout 4" image for the 256-bit kernel (dense_small_v4.cu): permuted k and output-row orders ----
             if (N % 16 == 0) {
@@ -144,7 +171,10 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
                     }
                 const bool exact = dev == 0.0;
                 const bool approx = (flags & SBP_DENSE_SYMMETRIZE) && dev <= 256.0 * 2.220446049250313e-16 * amax;
-                if (exact || approx) {
+                // the even/odd split halves the work; skipping zero fragments wins when more than half are zero
+                const bool prefer_skip = op->band > 0 && (2.0 * op->band + 1.0) / NT < 0.5;
+                if ((exact || approx) && !prefer_skip) {
+                    op->band = 0;
                     const int h = N / 2, NTH = N / 16, KSH = 2 * NTH;
                     const size_t FH = (size_t)KSH * NTH * 32;
                     std::vector<double> fs(2 * FH, 0.0);
@@ -218,6 +248,10 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
             cost += (double)w * (17.0 + 2.0 * R);
         }
         if (R == 4) cost *= 1.2;  // measured: 32 accumulators + operator prefetch cost occupancy (158 vs 124 registers)
+        // a tile is worked on by one warp per slice: too few slices leave the CTA's other warps idle (N = 101, R = 4
+        // is a single slice and ran 30% slower than R = 1 with its 4 slices)
+        const int nsl = (nrb + 31) / 32;
+        if (nsl < 4) cost *= 4.0 / nsl;
         if (cost < best_cost * 0.97) {  // prefer the smaller R unless the gain is real
             best_cost = cost;
             best_logR = logR;
@@ -628,6 +662,7 @@ int32_t sbp_op_advection1d_create(sbp_ctx* ctx, const sbp_op* D, const double* h
             qc[N + i] = w[i] * Da[i];
             qc[2 * (size_t)N + i] = h_a[i];
         }
+        op->sat_a0 = h_a[0], op->sat_aN = h_a[N - 1], op->sat_w0 = w[0], op->sat_wN = w[N - 1];
         rc = upload(&op->d_q_consts, qc);
         if (rc) goto fail;
     }
@@ -637,7 +672,7 @@ int32_t sbp_op_advection1d_create(sbp_ctx* ctx, const sbp_op* D, const double* h
             std::vector<double> cf((size_t)KS * 4, 0.0);
             for (int ks = 0; ks < KS; ks++)
                 for (int t = 0; t < 4; t++) {
-                    const int k = phys_k_host(ks, t);
+                    const int k = frag_k(D->layout, ks, t);
                     if (k < N) cf[ks * 4 + t] = h_a[k];
                 }
             rc = upload(&op->d_a, cf);
@@ -787,16 +822,26 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     SBP_REQUIRE(bc_stride == 0 || bc_stride >= 2, SBP_EDIM, "bc_stride must be 0 or >= 2");
     SBP_CUDA(cudaSetDevice(ctx->device));
     const sbp_op* D = op->inner;
+    // the SATs at the two end nodes are fused into the apply kernel (one pass, no second launch)
+    Sat1D sat;
+    sat.bc = bc;
+    sat.bc_stride = bc_stride;
+    sat.a0 = op->sat_a0, sat.aN = op->sat_aN, sat.w0 = op->sat_w0, sat.wN = op->sat_wN;
+    sat.enabled = 1;
+    bool fused = true;
     if (D->kind == SBP_OP_SPARSE)
-        rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a);
+        rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a, &sat);
     else if (D->sym && op->d_a == nullptr)
-        rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant());
+        rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant(), &sat);
     else if (is_small(D))
-        rc = launch_dense_small_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, op->d_a);
-    else
+        rc = launch_dense_small_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, op->d_a, &sat);
+    else {
         rc = launch_dense_gemm(ctx, D, dU, U, B, -1.0, 0.0);
+        fused = false;
+    }
     if (rc) return rc;
-    return launch_adv1d_epilogue(ctx, op, dU, U, B, bc, bc_stride, quantities, true);
+    if (fused && quantities == nullptr) return SBP_OK;
+    return launch_adv1d_epilogue(ctx, op, dU, U, B, bc, bc_stride, quantities, !fused);
 }
 
 int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,

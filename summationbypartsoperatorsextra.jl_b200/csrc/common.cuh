@@ -67,6 +67,9 @@ struct sbp_op {
     bool sym = false;          // centro-antisymmetric (even/odd split available)
     double* d_frag_sym = nullptr;  // [E | O] half-operator fragments (dense_small_sym.cu)
     double* d_wsym = nullptr;      // weights [w(j) | w(N-1-j)] in fragment k order
+    int layout = 2;                // fragment layout of d_frag (dense_small.cu): 2 paired-k (N % 8 == 0), 1 natural
+    int band = 0;                  // > 0: fragments with |k-pair - n-tile| > band are structurally zero (banded D)
+    double zero_frac = 0.0;        // fraction of structurally zero fragments
     double* d_frag4 = nullptr;     // fragment image in "layout 4" (256-bit accesses, dense_small_v4.cu), N % 16 == 0
     double* d_wfrag4 = nullptr;
     // sparse (SELL-32 slices)
@@ -88,14 +91,47 @@ struct sbp_op {
     double* d_bnd_tau = nullptr;
     double* d_a = nullptr;
     double* d_q_consts = nullptr;  // per-node constants for the analysis quantities
+    double sat_a0 = 1.0, sat_aN = 1.0, sat_w0 = 1.0, sat_wN = 1.0;  // 1D bundle: end speeds and end weights
 };
 
 namespace sbp {
+// Fused SATs of the upstream 1D semidiscretization: applied by the thread that owns row 0 / row N-1.
+//   du[0]   += (fl - a0*u0)/w0,   fl = godunov(bc_left, u0, a0)  = a0 > 0 ? a0*bc_left : a0*u0
+//   du[N-1] -= (fr - aN*uN)/wN,   fr = godunov(uN, bc_right, aN) = aN > 0 ? aN*uN     : aN*bc_right
+struct Sat1D {
+    const double* bc = nullptr;  // [left, right] per instance (stride bc_stride doubles) or shared (stride 0)
+    long long bc_stride = 0;
+    double a0 = 1.0, aN = 1.0, w0 = 1.0, wN = 1.0;
+    int enabled = 0;
+};
+#ifdef __CUDACC__
+// t0 = a0*u0 (as rounded by the reference's a .* u), returns the term ADDED to du[0]
+__device__ __forceinline__ double sat1d_left(const Sat1D& s, long long inst, double t0) {
+    const double lb = s.bc[inst * s.bc_stride];
+    const double fl = s.a0 > 0.0 ? s.a0 * lb : t0;
+    return (fl - t0) / s.w0;
+}
+__device__ __forceinline__ double sat1d_right(const Sat1D& s, long long inst, double tN) {
+    const double rb = s.bc[inst * s.bc_stride + 1];
+    const double fr = s.aN > 0.0 ? tN : s.aN * rb;
+    return -((fr - tN) / s.wN);
+}
+// same with the boundary value already in a register
+__device__ __forceinline__ double sat1d_left_v(const Sat1D& s, double lb, double t0) {
+    const double fl = s.a0 > 0.0 ? s.a0 * lb : t0;
+    return (fl - t0) / s.w0;
+}
+__device__ __forceinline__ double sat1d_right_v(const Sat1D& s, double rb, double tN) {
+    const double fr = s.aN > 0.0 ? tN : s.aN * rb;
+    return -((fr - tN) / s.wN);
+}
+#endif
 // kernel-family launchers (each in its own .cu)
 int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                            double beta, bool periodic_table, double* energy, double* energy_sum);
 int32_t launch_dense_small_sym(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
-                               double beta, double* energy, double* energy_sum, int variant);
+                               double beta, double* energy, double* energy_sum, int variant,
+                               const Sat1D* sat = nullptr);
 int32_t launch_dense_small_v4(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                               double beta, double* energy, double* energy_sum, int variant);
 int32_t launch_table_generic(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,

@@ -8,10 +8,21 @@
 //                                          (instance-contiguous layout == "row-major" A)
 //   B operand (col-major 4x8 fragments) = D^T, pre-permuted on the host into fragment order and
 //                                          staged once per CTA into shared memory with a TMA bulk copy
-//   C fragment: a lane ends up with 2 consecutive output nodes of one instance -> 128-bit stores.
-// The contraction order is free, so one 128-bit load (nodes 8kp+2t, 8kp+2t+1) feeds two k-steps.
-// A warp owns work items (tile of 8*MT slots, operator gi); the raw 128-bit loads of the NEXT item are issued
-// right after the current item's values are unpacked, so HBM latency hides behind the DMMA chain (PREFETCH).
+//   C fragment: a lane ends up with 2 output nodes of one instance.
+// The contraction order and the output-row order are free, so the host picks the fragment "layout" that gives the
+// widest aligned global accesses:
+//   layout 2 (N % 8 == 0):  k-step ks, lane t <-> node 8(ks>>1)+2t+(ks&1);  n-tile nt, column n <-> row 8nt+n
+//                           -> one 128-bit load feeds two k-steps, a lane stores 2 consecutive rows (128-bit)
+//   layout 1 (any N):       k-step ks, lane t <-> node 4ks+t;               column n <-> row 8nt+(n>>1)+4(n&1)
+//                           -> 64-bit accesses, the 4 lanes of a group cover 32 contiguous bytes per instance
+//   (layout 4, N % 16 == 0, 256-bit accesses: dense_small_v4.cu)
+// A warp owns work items (tile of 8*MT slots, operator gi); the raw loads of the NEXT item are issued right after the
+// current item's values are unpacked, so HBM latency hides behind the DMMA chain.
+// BAND: for banded operators (FSBP with `bandwidth`, finite-difference SBP operators stored dense as in the
+// reference) every fragment (k-pair kp, n-tile nt) with |kp - nt| > BAND is entirely zero; those DMMAs are removed
+// at compile time (a runtime bit-mask predicate was tried first: predicated-off DMMAs still cost their issue and the
+// kernel did not speed up).  The dropped products are exact zeros and the accumulation order of the remaining ones
+// is unchanged, so the result is bitwise the same as multiplying the stored zeros (for finite inputs).
 #include <algorithm>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -21,9 +32,9 @@ namespace sbp {
 struct DenseSmallParams {
     const double* __restrict__ U;
     double* __restrict__ dU;
-    const double* __restrict__ frag;   // G * KS*NT*32
-    const double* __restrict__ wfrag;  // G * KS*4  (weights in A-fragment k order) or nullptr
-    const double* __restrict__ cfrag;  // KS*4 column scaling (a .* u of the 1D advection) or nullptr
+    const double* __restrict__ frag;     // G * KS*NT*32
+    const double* __restrict__ wfrag;    // G * KS*4  (weights in A-fragment k order) or nullptr
+    const double* __restrict__ cfrag;    // KS*4 column scaling (a .* u of the 1D advection) or nullptr
     int N;
     int G;
     long long B;
@@ -31,34 +42,38 @@ struct DenseSmallParams {
     double beta;
     double* energy;   // per instance or nullptr
     double* partial;  // per-CTA energy partial sums or nullptr
+    Sat1D sat;        // fused 1D advection SATs (rows 0 and N-1)
 };
 
-// physical node index of logical (k-step ks, lane-in-group t)
-__host__ __device__ __forceinline__ int phys_k(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
+enum { MODE_VEC2 = 0, MODE_SCALAR2 = 1, MODE_SCALAR1 = 2 };
 
-// raw A data of one work item: MT m-tiles x NT 128-bit chunks per lane
-template <int NT, int MT, bool FULL>
+// raw A data of one work item: MT m-tiles x NT pairs (k-steps 2kp, 2kp+1) per lane
+template <int NT, int MT, int MODE>
 __device__ __forceinline__ void load_item(double2 (&raw)[MT][NT], const double* __restrict__ U, long long tile, int gi,
                                           int G, int g, int t, int N, long long B) {
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
         const long long inst = (tile * (8 * MT) + mt * 8 + g) * G + gi;
         const bool valid = inst < B;
-        const double* up = U + inst * N + 2 * t;
+        const double* up = U + inst * N;
 #pragma unroll
         for (int kp = 0; kp < NT; kp++) {
-            if (FULL) {
-                raw[mt][kp] = valid ? ldg_stream2(up + 8 * kp) : make_double2(0.0, 0.0);
-            } else {
+            if (MODE == MODE_VEC2) {
+                raw[mt][kp] = valid ? ldg_stream2(up + 8 * kp + 2 * t) : make_double2(0.0, 0.0);
+            } else if (MODE == MODE_SCALAR2) {
                 const int k0 = 8 * kp + 2 * t;
-                raw[mt][kp].x = (valid && k0 < N) ? ldg_stream1(up + 8 * kp) : 0.0;
-                raw[mt][kp].y = (valid && k0 + 1 < N) ? ldg_stream1(up + 8 * kp + 1) : 0.0;
+                raw[mt][kp].x = (valid && k0 < N) ? ldg_stream1(up + k0) : 0.0;
+                raw[mt][kp].y = (valid && k0 + 1 < N) ? ldg_stream1(up + k0 + 1) : 0.0;
+            } else {
+                const int k0 = 8 * kp + t;  // k-step 2kp -> node 8kp+t, k-step 2kp+1 -> node 8kp+4+t
+                raw[mt][kp].x = (valid && k0 < N) ? ldg_stream1(up + k0) : 0.0;
+                raw[mt][kp].y = (valid && k0 + 4 < N) ? ldg_stream1(up + k0 + 4) : 0.0;
             }
         }
     }
 }
 
-template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE, bool PREFETCH>
+template <int NT, int MT, int THREADS, int MODE, bool ENERGY, int BAND>
 __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams p) {
     constexpr int KS = 2 * NT;
     constexpr int FRAG = KS * NT * 32;
@@ -69,7 +84,8 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
 
     double* s_frag = smem;                          // G*FRAG
     double* s_wfrag = smem + (size_t)p.G * FRAG;    // G*KS*4 (if ENERGY)
-    double* s_cfrag = s_wfrag + (ENERGY ? p.G * KS * 4 : 0);
+    double* s_cfrag = s_wfrag + (ENERGY ? p.G * KS * 4 : 0);                          // KS*4 (if cfrag)
+    const bool cscale = p.cfrag != nullptr;
 
     // ---- stage the operator once per CTA: TMA bulk copies tracked by one mbarrier ----
     if (threadIdx.x == 0) {
@@ -89,7 +105,7 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
     }
     if (ENERGY)
         for (int i = threadIdx.x; i < p.G * KS * 4; i += THREADS) s_wfrag[i] = p.wfrag[i];
-    if (CSCALE)
+    if (cscale)
         for (int i = threadIdx.x; i < KS * 4; i += THREADS) s_cfrag[i] = p.cfrag[i];
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -107,11 +123,10 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
     long long tile = (long long)blockIdx.x * WARPS + warp;
     int gi = 0;
     double2 raw[MT][NT];
-    if (PREFETCH && tile < ntiles) load_item<NT, MT, FULL>(raw, p.U, tile, gi, G, g, t, N, B);
+    if (tile < ntiles) load_item<NT, MT, MODE>(raw, p.U, tile, gi, G, g, t, N, B);
 
     while (tile < ntiles) {
-        if (!PREFETCH) load_item<NT, MT, FULL>(raw, p.U, tile, gi, G, g, t, N, B);
-        // ---- A fragments: unpack (node 8kp+2t -> k-step 2kp, node 8kp+2t+1 -> k-step 2kp+1) ----
+        // ---- A fragments: unpack (.x -> k-step 2kp, .y -> k-step 2kp+1) ----
         double a[MT][KS];
         long long inst[MT];
 #pragma unroll
@@ -124,6 +139,19 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
             }
         }
         const int cur_gi = gi;
+        // fused 1D SATs: fetch the boundary data and the two end values of every instance NOW, so that their latency
+        // hides behind the DMMA chain (the lines were just requested by the fragment loads: L2 hits)
+        double sat_bl[MT], sat_br[MT], sat_u0[MT], sat_uN[MT];
+        if (p.sat.enabled) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const bool v = inst[mt] < B;
+                sat_bl[mt] = v ? p.sat.bc[inst[mt] * p.sat.bc_stride] : 0.0;
+                sat_br[mt] = v ? p.sat.bc[inst[mt] * p.sat.bc_stride + 1] : 0.0;
+                sat_u0[mt] = v ? p.U[inst[mt] * N] : 0.0;
+                sat_uN[mt] = v ? p.U[inst[mt] * N + N - 1] : 0.0;
+            }
+        }
         // next work item of this warp; its loads fly while the tensor pipe works on the current one
         long long ntile = tile;
         int ngi = gi + 1;
@@ -131,7 +159,7 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
             ngi = 0;
             ntile = tile + tstride;
         }
-        if (PREFETCH && ntile < ntiles) load_item<NT, MT, FULL>(raw, p.U, ntile, ngi, G, g, t, N, B);
+        if (ntile < ntiles) load_item<NT, MT, MODE>(raw, p.U, ntile, ngi, G, g, t, N, B);
 
         // ---- fused discrete energy  u' P u  (warp-shuffle reduction over the 4 lanes of a group) ----
         if (ENERGY) {
@@ -149,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
                 }
             }
         }
-        if (CSCALE) {
+        if (cscale) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
 #pragma unroll
@@ -166,35 +194,47 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
         for (int ks = 0; ks < KS; ks++) {
 #pragma unroll
             for (int nt = 0; nt < NT; nt++) {
-                const double b = bf[(ks * NT + nt) * 32];
+                if (BAND == 0 || ((ks >> 1) - nt <= BAND && nt - (ks >> 1) <= BAND)) {  // resolved at compile time
+                    const double b = bf[(ks * NT + nt) * 32];
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt][ks], b);
+                    for (int mt = 0; mt < MT; mt++) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt][ks], b);
+                }
             }
         }
-        // ---- epilogue: lane owns nodes (8nt+2t, 8nt+2t+1) of instance g of each m-tile ----
+        // ---- epilogue: lane owns 2 output nodes per n-tile of instance g of each m-tile ----
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
             if (inst[mt] >= B) continue;
-            double* yp = p.dU + inst[mt] * N + 2 * t;
+            double* yp = p.dU + inst[mt] * N;
 #pragma unroll
             for (int nt = 0; nt < NT; nt++) {
                 double y0 = alpha * c[mt][nt][0], y1 = alpha * c[mt][nt][1];
-                if (FULL) {
+                if (p.sat.enabled && (nt == 0 || nt == NT - 1)) {
+                    // rows owned by this lane in this n-tile (see the layouts above)
+                    const int r0 = (MODE == MODE_SCALAR1) ? 8 * nt + t : 8 * nt + 2 * t;
+                    const int r1 = (MODE == MODE_SCALAR1) ? r0 + 4 : r0 + 1;
+                    if (r0 == 0) y0 += sat1d_left_v(p.sat, sat_bl[mt], p.sat.a0 * sat_u0[mt]);
+                    if (r0 == N - 1) y0 += sat1d_right_v(p.sat, sat_br[mt], p.sat.aN * sat_uN[mt]);
+                    if (r1 == N - 1) y1 += sat1d_right_v(p.sat, sat_br[mt], p.sat.aN * sat_uN[mt]);
+                }
+                if (MODE == MODE_VEC2) {
+                    double* q = yp + 8 * nt + 2 * t;
                     if (beta != 0.0) {
-                        const double2 o = *reinterpret_cast<const double2*>(yp + 8 * nt);
+                        const double2 o = *reinterpret_cast<const double2*>(q);
                         y0 = fma(beta, o.x, y0);
                         y1 = fma(beta, o.y, y1);
                     }
-                    stg_stream2(yp + 8 * nt, y0, y1);
+                    stg_stream2(q, y0, y1);
                 } else {
-                    const int r0 = 8 * nt + 2 * t;
+                    const int r0 = (MODE == MODE_SCALAR2) ? 8 * nt + 2 * t : 8 * nt + t;
+                    const int r1 = (MODE == MODE_SCALAR2) ? r0 + 1 : r0 + 4;
                     if (r0 < N) {
-                        if (beta != 0.0) y0 = fma(beta, yp[8 * nt], y0);
-                        stg_stream1(yp + 8 * nt, y0);
+                        if (beta != 0.0) y0 = fma(beta, yp[r0], y0);
+                        stg_stream1(yp + r0, y0);
                     }
-                    if (r0 + 1 < N) {
-                        if (beta != 0.0) y1 = fma(beta, yp[8 * nt + 1], y1);
-                        stg_stream1(yp + 8 * nt + 1, y1);
+                    if (r1 < N) {
+                        if (beta != 0.0) y1 = fma(beta, yp[r1], y1);
+                        stg_stream1(yp + r1, y1);
                     }
                 }
             }
@@ -214,11 +254,11 @@ __global__ void __launch_bounds__(THREADS) k_dense_small(const DenseSmallParams 
     }
 }
 
-template <int NT, int MT, int THREADS, bool FULL, bool ENERGY, bool CSCALE, bool PREFETCH>
+template <int NT, int MT, int THREADS, int MODE, bool ENERGY, int BAND>
 static int32_t launch_variant(sbp_ctx* ctx, const DenseSmallParams& p, double* energy_sum) {
     constexpr int KS = 2 * NT;
-    auto kern = k_dense_small<NT, MT, THREADS, FULL, ENERGY, CSCALE, PREFETCH>;
-    size_t smem = (size_t)p.G * KS * NT * 32 * 8 + (ENERGY ? (size_t)p.G * KS * 4 * 8 : 0) + (CSCALE ? KS * 4 * 8 : 0);
+    auto kern = k_dense_small<NT, MT, THREADS, MODE, ENERGY, BAND>;
+    size_t smem = (size_t)p.G * KS * NT * 32 * 8 + (ENERGY ? (size_t)p.G * KS * 4 * 8 : 0) + (p.cfrag ? KS * 4 * 8 : 0);
     SBP_REQUIRE((int64_t)smem <= ctx->smem_optin - 1024, SBP_EUNSUPPORTED,
                 "operator table needs %zu bytes of shared memory (> %lld available)", smem,
                 (long long)ctx->smem_optin);
@@ -244,43 +284,29 @@ static int32_t launch_variant(sbp_ctx* ctx, const DenseSmallParams& p, double* e
 }
 
 template <int NT>
-static int32_t dispatch_nt(sbp_ctx* ctx, const DenseSmallParams& p, bool full, bool energy, bool cscale,
-                           double* energy_sum, int variant) {
+static int32_t dispatch_nt(sbp_ctx* ctx, const DenseSmallParams& p, int mode, bool energy, int band,
+                           double* energy_sum) {
     // m-tiles per warp iteration: keep ~64 accumulator doubles per lane at most
     constexpr int MT = (NT <= 2) ? 4 : (NT <= 8 ? 2 : 1);
     constexpr int TH = 128;
-    // variant bit0: software prefetch of the next work item (tuning knob SBP_DS_VARIANT, default on)
-#define SBP_DS(F, E, C)                                                                 \
-    return (variant & 1) ? launch_variant<NT, MT, TH, F, E, C, true>(ctx, p, energy_sum) \
-                         : launch_variant<NT, MT, TH, F, E, C, false>(ctx, p, energy_sum)
-    if (full) {
-        if (energy) {
-            if (cscale) SBP_DS(true, true, true);
-            SBP_DS(true, true, false);
-        }
-        if (cscale) SBP_DS(true, false, true);
-        SBP_DS(true, false, false);
-    }
-    if (energy) {
-        if (cscale) SBP_DS(false, true, true);
-        SBP_DS(false, true, false);
-    }
-    if (cscale) SBP_DS(false, false, true);
-    SBP_DS(false, false, false);
+    // band variants exist only where they remove work (NT >= 4) and for the apply without fused energy
+    constexpr int B1 = (NT >= 4) ? 1 : 0, B2 = (NT >= 6) ? 2 : 0;
+#define SBP_DS(M)                                                                                      \
+    do {                                                                                               \
+        if (energy) return launch_variant<NT, MT, TH, M, true, 0>(ctx, p, energy_sum);                 \
+        if (band == 1 && B1) return launch_variant<NT, MT, TH, M, false, B1>(ctx, p, energy_sum);      \
+        if (band == 2 && B2) return launch_variant<NT, MT, TH, M, false, B2>(ctx, p, energy_sum);      \
+        return launch_variant<NT, MT, TH, M, false, 0>(ctx, p, energy_sum);                            \
+    } while (0)
+    if (mode == MODE_VEC2) SBP_DS(MODE_VEC2);
+    if (mode == MODE_SCALAR2) SBP_DS(MODE_SCALAR2);
+    SBP_DS(MODE_SCALAR1);
 #undef SBP_DS
 }
 
-static int ds_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SBP_DS_VARIANT");
-        v = e ? atoi(e) & 1 : 1;
-    }
-    return v;
-}
-
 int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
-                              double beta, double* energy, double* energy_sum, const double* cfrag) {
+                              double beta, double* energy, double* energy_sum, const double* cfrag,
+                              const Sat1D* sat) {
     DenseSmallParams p;
     p.U = U;
     p.dU = dU;
@@ -294,26 +320,31 @@ int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const 
     p.beta = beta;
     p.energy = energy;
     p.partial = nullptr;
+    if (sat) p.sat = *sat;
     const bool want_energy = (energy != nullptr) || (energy_sum != nullptr);
     SBP_REQUIRE(!want_energy || op->d_wfrag, SBP_EINVAL, "energy requested but the operator has no weights");
-    // 256-bit variant (N % 16 == 0, 32-byte aligned batches, no column scaling); SBP_DS_V4 = -1 disables it,
-    // otherwise its low bits select the variant (bit0 prefetch, bit1 fewer m-tiles per item)
+    const int band = op->band;  // 0 = full operator
+    const bool skip = band > 0 && !want_energy;
+    // 256-bit variant (N % 16 == 0, 32-byte aligned batches, no column scaling, no zero-fragment skipping);
+    // SBP_DS_V4 = -1 disables it, otherwise its low bits select the variant (dense_small_v4.cu)
     static int v4 = -2;
     if (v4 == -2) {
         const char* e = getenv("SBP_DS_V4");
         v4 = e ? atoi(e) : 1;
     }
-    if (v4 >= 0 && op->d_frag4 && cfrag == nullptr && ((reinterpret_cast<uintptr_t>(U) & 31) == 0) &&
+    if (v4 >= 0 && !skip && sat == nullptr && op->d_frag4 && cfrag == nullptr &&
+        ((reinterpret_cast<uintptr_t>(U) & 31) == 0) &&
         ((reinterpret_cast<uintptr_t>(dU) & 31) == 0))
         return launch_dense_small_v4(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, v4);
-    const bool full = (op->N == op->NT * 8) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(dU) & 15) == 0);
-    const bool cs = cfrag != nullptr;
-    const int variant = ds_variant();
+    int mode;
+    if (op->layout == 1)
+        mode = MODE_SCALAR1;
+    else
+        mode = (((reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(dU)) & 15) == 0) ? MODE_VEC2 : MODE_SCALAR2;
     switch (op->NT) {
 #define SBP_CASE(n) \
     case n:         \
-        return dispatch_nt<n>(ctx, p, full, want_energy, cs, energy_sum, variant);
+        return dispatch_nt<n>(ctx, p, mode, want_energy, band, energy_sum);
         SBP_CASE(1)
         SBP_CASE(2)
         SBP_CASE(3)
@@ -338,7 +369,7 @@ int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const 
 
 int32_t launch_dense_small(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                            double beta, bool /*periodic_table*/, double* energy, double* energy_sum) {
-    return launch_dense_small_ex(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, nullptr);
+    return launch_dense_small_ex(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, nullptr, nullptr);
 }
 
 }  // namespace sbp

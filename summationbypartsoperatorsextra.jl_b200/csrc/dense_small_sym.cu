@@ -24,6 +24,7 @@ struct DenseSymParams {
     double beta;
     double* energy;
     double* partial;
+    Sat1D sat;  // fused 1D advection SATs (unit speed only: a variable speed breaks the symmetry)
 };
 
 __device__ __forceinline__ int phys_k_sym(int ks, int t) { return 8 * (ks >> 1) + 2 * t + (ks & 1); }
@@ -121,6 +122,22 @@ __global__ void __launch_bounds__(THREADS) k_dense_small_sym(const DenseSymParam
                 }
             }
         }
+        // end values for the fused SATs: lane t == 0 holds u[0] (lo.x) and u[N-1] (hi.y) of its instance
+        double u_first[MT], u_last[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            u_first[mt] = raw.lo[mt][0].x;
+            u_last[mt] = raw.hi[mt][0].y;
+        }
+        double sat_bl[MT], sat_br[MT];  // boundary data fetched early: latency hides behind the DMMA chain
+        if (p.sat.enabled) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const long long inst = tile * (8 * MT) + mt * 8 + g;
+                sat_bl[mt] = inst < B ? p.sat.bc[inst * p.sat.bc_stride] : 0.0;
+                sat_br[mt] = inst < B ? p.sat.bc[inst * p.sat.bc_stride + 1] : 0.0;
+            }
+        }
         // the raw registers are dead now: refill them with the next tile while the tensor pipe works
         const long long next = tile + tstride;
         if (PREFETCH && next < ntiles) load_raw<NTH, MT>(raw, p.U, next, g, t, N, B);
@@ -169,6 +186,10 @@ __global__ void __launch_bounds__(THREADS) k_dense_small_sym(const DenseSymParam
                 double y1 = alpha * (cp[mt][nt][1] + cq[mt][nt][1]);
                 double z0 = alpha * (cq[mt][nt][0] - cp[mt][nt][0]);  // row N-1-i0
                 double z1 = alpha * (cq[mt][nt][1] - cp[mt][nt][1]);  // row N-2-i0
+                if (p.sat.enabled && nt == 0 && t == 0) {              // i0 == 0: rows 0 and N-1
+                    y0 += sat1d_left_v(p.sat, sat_bl[mt], p.sat.a0 * u_first[mt]);
+                    z0 += sat1d_right_v(p.sat, sat_br[mt], p.sat.aN * u_last[mt]);
+                }
                 if (beta != 0.0) {
                     const double2 o = *reinterpret_cast<const double2*>(yp + i0);
                     const double2 m = *reinterpret_cast<const double2*>(yp + N - 2 - i0);
@@ -240,8 +261,9 @@ static int32_t dispatch_sym(sbp_ctx* ctx, const DenseSymParams& p, bool energy, 
 }
 
 int32_t launch_dense_small_sym(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
-                               double beta, double* energy, double* energy_sum, int variant) {
+                               double beta, double* energy, double* energy_sum, int variant, const Sat1D* sat) {
     DenseSymParams p;
+    if (sat) p.sat = *sat;
     p.U = U;
     p.dU = dU;
     p.frag = op->d_frag_sym;

@@ -43,6 +43,7 @@ struct SparseParams {
     const double* __restrict__ g;
     long long g_stride;
     int vec_ok;                          // output rows of a lane may be stored with one vector store
+    Sat1D sat;                           // fused 1D advection SATs (rows 0 and N-1); the staged tile holds a .* u
 };
 
 constexpr int kT = 8;  // instances per tile
@@ -143,6 +144,11 @@ __global__ void __launch_bounds__(kSparseMaxThreads) k_sparse(const SparseParams
         for (int s = warp; s < p.n_slices; s += WARPS) {
             const int rb = s * 32 + lane;
             const int beg = p.slice_ptr[s], end = p.slice_ptr[s + 1];
+            // boundary slices of a 1D advection RHS: request the boundary data now, use it after the gather loop
+            const bool has0 = (s == 0), hasN = (((N - 1) >> LOGR) >> 5) == s;  // warp-uniform
+            double sat_bc = 0.0;
+            if (p.sat.enabled && (has0 || hasN) && lane < 2 * kT && (lane & (kT - 1)) < nb)
+                sat_bc = p.sat.bc[(b0 + (lane & (kT - 1))) * p.sat.bc_stride + ((lane >> 3) & 1)];
             double acc[R][kT];
 #pragma unroll
             for (int r = 0; r < R; r++)
@@ -209,6 +215,29 @@ __global__ void __launch_bounds__(kSparseMaxThreads) k_sparse(const SparseParams
                 for (int r = 0; r < R; r++) v0[r] = w0[r], v1[r] = w1[r];
                 cp = cpn, vp = vpn;
             }
+            // ---- fused 1D SATs (rows 0 and N-1): the slice(s) holding those rows compute the 2 x kT terms with 16 lanes in
+            //      parallel (one boundary-data load and one division each) and hand them to the row owners by shuffle ----
+            double sat_l[kT], sat_r[kT];
+            if (p.sat.enabled && (has0 || hasN)) {
+                const int tt = lane & (kT - 1), side = (lane >> 3) & 1;
+                double satv = 0.0;
+                if (lane < 2 * kT && tt < nb && (side ? hasN : has0)) {
+                    const int row = side ? N - 1 : 0;
+                    double tj;  // a_j * u_j exactly as the reference's a .* u (the staged tile is column scaled)
+                    if (SMEM) {
+                        const int slot = node_slot<LOGR>(row);
+                        tj = s_u[slot * kT + (((tt >> 1) ^ slot_swz<LOGR>(slot)) << 1) + (tt & 1)];
+                    } else {
+                        tj = p.U[(b0 + tt) * N + row] * (p.colscale ? p.colscale[row] : 1.0);
+                    }
+                    satv = side ? sat1d_right_v(p.sat, sat_bc, tj) : sat1d_left_v(p.sat, sat_bc, tj);
+                }
+#pragma unroll
+                for (int t = 0; t < kT; t++) {
+                    sat_l[t] = __shfl_sync(0xffffffffu, satv, t);
+                    sat_r[t] = __shfl_sync(0xffffffffu, satv, kT + t);
+                }
+            }
             // ---- epilogue: alpha, fused SAT on inflow rows, beta, vector store of the lane's R contiguous rows ----
             const int row0 = rb * R;
             if (row0 < N) {
@@ -241,6 +270,10 @@ __global__ void __launch_bounds__(kSparseMaxThreads) k_sparse(const SparseParams
                                 uj = p.U[(b0 + t) * N + row0 + r];
                             }
                             y[r] += satb[r] * (uj - p.g[(b0 + t) * p.g_stride + row0 + r]);
+                        }
+                        if (p.sat.enabled && (has0 || hasN)) {
+                            if (row0 + r == 0) y[r] += sat_l[t];
+                            if (row0 + r == N - 1) y[r] += sat_r[t];
                         }
                     }
                     const bool full = row0 + R <= N;
@@ -301,7 +334,7 @@ static int32_t launch_sparse_r(sbp_ctx* ctx, const SparseParams& p) {
 
 int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                          double beta, const sbp_op* adv, const double* g, int64_t g_stride,
-                         const double* colscale) {
+                         const double* colscale, const Sat1D* sat) {
     SparseParams p;
     p.U = U;
     p.dU = dU;
@@ -315,6 +348,7 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
     p.bdiag = adv ? adv->d_b : nullptr;
     p.g = g;
     p.g_stride = g_stride;
+    if (sat) p.sat = *sat;
     const int R = 1 << op->logR;
     p.n_slots = ((op->N + 2 * R - 1) / (2 * R)) * (2 * R);
     // vector stores need every lane's R rows aligned to R*8 bytes for every instance
@@ -358,7 +392,7 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
 
 int32_t launch_sparse(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                       double beta, const sbp_op* adv, const double* g, int64_t g_stride, double* quantities) {
-    int32_t rc = launch_sparse_ex(ctx, op, dU, U, B, alpha, beta, adv, g, g_stride, nullptr);
+    int32_t rc = launch_sparse_ex(ctx, op, dU, U, B, alpha, beta, adv, g, g_stride, nullptr, nullptr);
     if (rc) return rc;
     if (adv && quantities) return launch_adv2d_epilogue(ctx, adv, dU, U, B, g, g_stride, quantities, false);
     return SBP_OK;

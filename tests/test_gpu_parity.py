@@ -88,6 +88,36 @@ def test_even_odd_kernel_equals_general_kernel(ctx, N):
     assert rel_err(a.to_host(), O.apply_batch(D.basis.D, U, D.jac)) <= TOL
 
 
+@pytest.mark.parametrize("order,N", [(2, 40), (4, 96), (4, 101), (4, 104), (2, 127), (4, 128)])
+def test_banded_dense_operator_skips_zero_fragments(ctx, order, N):
+    """Banded FD-SBP operators stored dense (as the reference stores them) on the smem-resident DMMA path: all-zero
+    fragments are skipped.  Skipping only drops exact-zero products, so the result is BITWISE equal to multiplying the
+    stored zeros (DENSE_NO_SKIP), and both match the oracle; odd N exercises the 64-bit fragment layout."""
+    D = S.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
+    D.storage = "dense"
+    Dn = S.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
+    Dn.storage = "dense"
+    Dn.dense_flags = S._lib.DENSE_NO_SKIP | S._lib.DENSE_NO_SYMMETRY
+    B = 2049
+    U, Y0 = rand_batch(B, N, 7), rand_batch(B, N, 8)
+    u = ctx.upload(U)
+    a, b = ctx.upload(Y0), ctx.upload(Y0)
+    S.mul_(a, D, u, 1.5, -0.5)
+    S.mul_(b, Dn, u, 1.5, -0.5)
+    ref = O.apply_batch(D.Matrix(), U, 1.5, -0.5, Y0)
+    assert rel_err(a.to_host(), ref) <= TOL and rel_err(b.to_host(), ref) <= TOL
+    if N % 16:  # same fragment layout on both sides (N % 16 == 0 sends the unbanded operator to the 256-bit kernel)
+        assert np.array_equal(a.to_host(), b.to_host())
+    assert rel_err(a.to_host(), b.to_host()) <= 1e-14
+    assert D.device_op(ctx).info()["kernel"] == "dmma_smem"  # narrow band: skipping beats the even/odd split
+    # the same operator through the sparse kernel
+    Ds = S.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
+    Ds.storage = "sparse"
+    c = ctx.upload(Y0)
+    S.mul_(c, Ds, u, 1.5, -0.5)
+    assert rel_err(c.to_host(), ref) <= TOL
+
+
 def test_symmetrize_flag(ctx):
     """A Legendre matrix that is centro-antisymmetric only up to rounding: exact detection declines, the opt-in flag
     accepts and stays within the documented perturbation."""

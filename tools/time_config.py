@@ -59,6 +59,16 @@ def main():
         def step(i):
             S._lib.check(lib.sbp_apply_table(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, None,
                                              1.0, 0.0, C.c_void_p(E.data_ptr()), C.c_void_p(E.data_ptr() + 8 * B)))
+    elif args.workload == "banded":  # plain mul! with a banded FD-SBP operator (no SAT epilogue)
+        N, B = (args.n if args.n != 64 else 101), 1 << 19
+        D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        D1.storage = "dense" if os.environ.get("SBP_BENCH_DENSE") else "sparse"
+        op = D1.device_op(ctx)
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+
+        def step(i):
+            S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
     elif args.workload == "config5":
         N, B = 4096, 1 << (args.batch_log2 if args.batch_log2 != 20 else 13)
         rng = np.random.default_rng(0)
@@ -94,9 +104,11 @@ def main():
                 storage="sparse")
             N = Dm.N
         else:  # config 1 batched: banded 1D operator N = 101, SAT at both ends
-            N, B = 101, 1 << 19
+            N, B = (args.n if args.n != 64 else 101), 1 << 19
             D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
-            D1.storage = "sparse"
+            D1.storage = "dense" if os.environ.get("SBP_BENCH_DENSE") else "sparse"
+            if args.nosym:
+                D1.dense_flags = S._lib.DENSE_NO_SYMMETRY
             semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False,
                                                                           lambda t: 0.3, lambda t: 0.0)
         U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
