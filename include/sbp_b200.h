@@ -142,6 +142,7 @@ int32_t sbp_op_info(const sbp_op* op, int32_t* kind, int32_t* N, int32_t* G, int
 #define SBP_KERNEL_DGEMM_TILED 3   /* large N: tiled DMMA DGEMM, operator streamed through L2          */
 #define SBP_KERNEL_CSR_SMEM 4      /* sparse: instance tile staged in smem, CSR rows per thread        */
 #define SBP_KERNEL_TABLE 5
+#define SBP_KERNEL_BSR_DMMA 6      /* sparse: 8x4 operator fragments on the FP64 tensor cores, node ring in smem */
 
 /* ---- hot path --------------------------------------------------------------------------- */
 

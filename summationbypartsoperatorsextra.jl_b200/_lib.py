@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 SBP_OK, SBP_EINVAL, SBP_EDIM, SBP_ECUDA, SBP_ENOMEM, SBP_ENCCL, SBP_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 OP_DENSE, OP_SPARSE, OP_TABLE, OP_ADVECTION2D, OP_ADVECTION1D = 1, 2, 3, 4, 5
 DENSE_AUTO, DENSE_FORCE_GEMM, DENSE_NO_SYMMETRY, DENSE_SYMMETRIZE, DENSE_NO_SKIP = 0, 1, 2, 4, 8
-KERNEL_NAMES = {1: "dmma_smem", 2: "dmma_smem_sym", 3: "dgemm_tiled", 4: "csr_smem", 5: "table_generic"}
+KERNEL_NAMES = {1: "dmma_smem", 2: "dmma_smem_sym", 3: "dgemm_tiled", 4: "csr_smem", 5: "table_generic", 6: "bsr_dmma"}
 NCCL_ID_BYTES = 128
 
 

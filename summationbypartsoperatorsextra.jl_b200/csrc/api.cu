@@ -308,6 +308,118 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
     return upload(&op->d_sell_val, v);
 }
 
+// Block-sparse DMMA image (bsr.cu): row blocks of 8 rows; the sorted union of a block's columns is cut into fragments
+// of 4 columns (the last one padded with a repeated column and zero values).  Chunks of 4 row blocks define the node
+// window [lo_c, hi_c) that must be resident while the chunk is multiplied; W[d] is the ring size that lets the nodes of
+// the next d chunks stream in while a chunk is being consumed (the stream continues across the tiles of a CTA with a
+// period of Np = N rounded up to even, plus a gap of two slots).
+static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, const std::vector<int>& col,
+                         const std::vector<double>& val) {
+    constexpr int CH = 4;  // == kBsrCH
+    const int nrb = (N + 7) / 8, nch = (nrb + CH - 1) / CH;
+    std::vector<int> rbptr(nrb + 1, 0), pos;
+    std::vector<double> frag;
+    std::vector<int> cmin(nch, N), cmax(nch, 0);
+    for (int rb = 0; rb < nrb; rb++) {
+        std::vector<int> u;
+        const int r_end = std::min(N, rb * 8 + 8);
+        for (int r = rb * 8; r < r_end; r++)
+            for (int j = rowptr[r]; j < rowptr[r + 1]; j++) u.push_back(col[j]);
+        std::sort(u.begin(), u.end());
+        u.erase(std::unique(u.begin(), u.end()), u.end());
+        // Fragments of 4 columns.  The A-operand gather of a fragment is bank-conflict free iff its 4 columns differ
+        // mod 4 (rows of a box are 36 = 4 (mod 16) doubles apart), so columns are dealt from 4 residue buckets, the
+        // fullest first; a fragment short of columns repeats one of its own (same address => broadcast, value 0).
+        const int nf = ((int)u.size() + 3) / 4;
+        const size_t f0 = frag.size() / 32;
+        frag.resize((f0 + nf) * 32, 0.0);
+        pos.resize((f0 + nf) * 4, 0);
+        std::vector<int> where(u.size(), 0);  // union index -> 4 * fragment + t
+        {
+            std::vector<int> bucket[4];
+            for (int k = (int)u.size() - 1; k >= 0; k--) bucket[u[k] & 3].push_back(k);  // pop_back yields ascending
+            for (int f = 0; f < nf; f++) {
+                int taken = 0, cols[4];
+                int order[4] = {0, 1, 2, 3};
+                std::sort(order, order + 4, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
+                for (int pass = 0; pass < 4 && taken < 4; pass++)
+                    for (int q = 0; q < 4 && taken < 4; q++) {
+                        std::vector<int>& bk = bucket[order[q]];
+                        // later passes only run when fewer than 4 residue classes are left
+                        if (!bk.empty()) {
+                            cols[taken++] = bk.back();
+                            bk.pop_back();
+                        }
+                    }
+                for (int t = 0; t < 4; t++) {
+                    const int k = cols[t < taken ? t : 0];
+                    pos[(f0 + f) * 4 + t] = u[k];
+                    if (t < taken) where[k] = 4 * f + t;
+                }
+            }
+        }
+        for (int r = rb * 8; r < r_end; r++)
+            for (int j = rowptr[r]; j < rowptr[r + 1]; j++) {
+                const int k = (int)(std::lower_bound(u.begin(), u.end(), col[j]) - u.begin());
+                const int w = where[k];
+                frag[(f0 + w / 4) * 32 + (size_t)(r - rb * 8) * 4 + (w & 3)] += val[j];  // lane = 4*g + t
+            }
+        rbptr[rb + 1] = (int)(f0 + nf);
+        const int c = rb / CH;
+        // the chunk's own rows are part of its window (the SAT epilogues read u_j from the ring)
+        cmin[c] = std::min(cmin[c], rb * 8);
+        cmax[c] = std::max(cmax[c], r_end);
+        if (!u.empty()) {
+            cmin[c] = std::min(cmin[c], u.front());
+            cmax[c] = std::max(cmax[c], u.back() + 1);
+        }
+    }
+    // windows in units of TMA boxes (kBsrBX nodes): boxes [0, bhi[c]) resident for chunk c, none below blo[c] needed later
+    constexpr int BX = kBsrBX;
+    std::vector<int> blo(nch), bhi(nch);
+    for (int c = 0, m = 0; c < nch; c++) {
+        m = std::max(m, cmax[c]);
+        bhi[c] = (m + BX - 1) / BX;
+    }
+    for (int c = nch - 1, m = N; c >= 0; c--) {
+        m = std::min(m, cmin[c]);
+        blo[c] = m / BX;
+    }
+    for (int rb = 0; rb < nrb; rb++)
+        for (int f = rbptr[rb] * 4; f < rbptr[rb + 1] * 4; f++) {
+            const int n = pos[f];
+            pos[f] = ((n / BX - blo[rb / CH]) << 8) | (n % BX);
+        }
+    // ring sizes: in the virtual box stream (tile k occupies boxes [k*nbt, (k+1)*nbt)) the boxes of item s may only
+    // overwrite slots that no item >= s - d still needs
+    const int nbt = (N + BX - 1) / BX;
+    int maxf = 1;
+    for (int c = 0; c < nch; c++) maxf = std::max(maxf, rbptr[std::min(nrb, c * CH + CH)] - rbptr[c * CH]);
+    for (int d = 0; d < 4; d++) {
+        long long need = 1;
+        const int items = nch * (d + 2);
+        for (int s = 0; s < items; s++) {
+            const int sb = std::max(0, s - d);
+            const long long vhi = (long long)(s / nch) * nbt + bhi[s % nch];
+            const long long vlo = (long long)(sb / nch) * nbt + blo[sb % nch];
+            need = std::max(need, vhi - vlo);
+        }
+        op->bsr_nbox[d] = (int)need;
+    }
+    op->bsr_maxf = maxf;
+    op->bsr_frags = (int64_t)frag.size() / 32;
+    if (frag.empty()) {
+        frag.assign(32, 0.0);
+        pos.assign(4, 0);
+    }
+    int32_t rc = upload(&op->d_bsr_val, frag);
+    if (!rc) rc = upload(&op->d_bsr_pos, pos);
+    if (!rc) rc = upload(&op->d_bsr_rbptr, rbptr);
+    if (!rc) rc = upload(&op->d_bsr_hi, bhi);
+    if (!rc) rc = upload(&op->d_bsr_lo, blo);
+    return rc;
+}
+
 // ---- NCCL through dlopen (no link-time dependency; torch's bundled libnccl is reused when loaded) -----
 struct Id128 {
     char b[128];
@@ -496,7 +608,8 @@ int32_t sbp_op_destroy(sbp_op* op) {
     void* ptrs[] = {op->d_D,         op->d_frag,     op->d_wfrag,    op->d_w,        op->d_frag_sym, op->d_rowptr,
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
-                    op->d_frag4,     op->d_wfrag4};
+                    op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbptr, op->d_bsr_hi,
+                    op->d_rbmask,    op->d_bsr_lo};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -554,6 +667,13 @@ int32_t sbp_op_sparse_create(sbp_ctx* ctx, int32_t N, const int32_t* h_rowptr, c
     std::vector<int> rp(h_rowptr, h_rowptr + N + 1), col(h_col, h_col + nnz);
     std::vector<double> val(h_val, h_val + nnz);
     int32_t rc = build_sell(op, N, rp, col, val);
+    if (!rc) rc = build_bsr(op, N, rp, col, val);
+    if (!rc) {
+        // kernel choice (SBP_SPARSE_KERNEL=sell|bsr overrides): the tensor-core kernel whenever a tile fits in smem
+        const char* e = getenv("SBP_SPARSE_KERNEL");
+        const bool want_bsr = e ? (strcmp(e, "bsr") == 0) : true;
+        if (want_bsr && bsr_available(ctx, op)) op->variant = SBP_KERNEL_BSR_DMMA;
+    }
     if (!rc && h_w) {
         std::vector<double> w(h_w, h_w + N);
         rc = upload(&op->d_w, w);
@@ -611,6 +731,12 @@ int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h
     for (int i = 0; i < Nb; i++) qc[2 * (size_t)N + h_bnd_node[i]] += h_bnd_tau[i];  // :98-105
     int32_t rc = upload(&op->d_b, b);
     if (!rc) rc = upload(&op->d_mode, mode);
+    if (!rc && A->variant == SBP_KERNEL_BSR_DMMA) {
+        std::vector<int> rbmask((N + 7) / 8, 0);
+        for (int i = 0; i < N; i++)
+            if (h_mode[i] == 1) rbmask[i >> 3] |= 1 << (i & 7);
+        rc = upload(&op->d_rbmask, rbmask);
+    }
     if (!rc) rc = upload(&op->d_q_consts, qc);
     if (!rc) {
         std::vector<double> w(h_w, h_w + N);
@@ -741,6 +867,7 @@ int32_t sbp_apply(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, i
             if (is_small(op)) return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, nullptr, nullptr);
             return launch_table_generic(ctx, op, dU, U, B, nullptr, alpha, beta, nullptr, nullptr);
         case SBP_OP_SPARSE:
+            if (bsr_can_run(op, U)) return launch_bsr(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, 0, nullptr);
             return launch_sparse(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, 0, nullptr);
         default:
             set_error("sbp_apply: operator kind %d is a semidiscretization bundle; use sbp_rhs_*", op->kind);
@@ -807,6 +934,11 @@ int32_t sbp_rhs_advection2d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     SBP_REQUIRE(g_stride == 0 || g_stride >= op->N, SBP_EDIM, "g_stride must be 0 or >= N");
     SBP_CUDA(cudaSetDevice(ctx->device));
     const sbp_op* A = op->inner;
+    if (A->kind == SBP_OP_SPARSE && bsr_can_run(A, U)) {
+        rc = launch_bsr(ctx, A, dU, U, B, -1.0, 0.0, op, g, g_stride, nullptr);
+        if (rc || !quantities) return rc;
+        return launch_adv2d_epilogue(ctx, op, dU, U, B, g, g_stride, quantities, false);
+    }
     if (A->kind == SBP_OP_SPARSE) return launch_sparse(ctx, A, dU, U, B, -1.0, 0.0, op, g, g_stride, quantities);
     rc = sbp_apply(ctx, A, dU, U, B, -1.0, 0.0);
     if (rc) return rc;
@@ -829,7 +961,9 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     sat.a0 = op->sat_a0, sat.aN = op->sat_aN, sat.w0 = op->sat_w0, sat.wN = op->sat_wN;
     sat.enabled = 1;
     bool fused = true;
-    if (D->kind == SBP_OP_SPARSE)
+    if (D->kind == SBP_OP_SPARSE && bsr_can_run(D, U) && op->d_a == nullptr)
+        rc = launch_bsr(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, &sat);
+    else if (D->kind == SBP_OP_SPARSE)
         rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a, &sat);
     else if (D->sym && op->d_a == nullptr)
         rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant(), &sat);

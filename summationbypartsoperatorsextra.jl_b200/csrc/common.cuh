@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...);
         }                                \
     } while (0)
 
+constexpr int kBsrBX = 36;  // nodes per TMA box of the block-sparse kernel: 36 = 4 (mod 16) doubles => conflict-free gathers
 constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
 
 }  // namespace sbp
@@ -82,6 +83,15 @@ struct sbp_op {
     int* d_sell_col = nullptr;
     double* d_sell_val = nullptr;
     int max_row_nnz = 0;
+    // sparse, block-sparse DMMA image (bsr.cu): row blocks of 8 rows, fragments of 4 gathered columns
+    double* d_bsr_val = nullptr;  // [fragment][32] B-operand fragments (row g, column t)
+    int* d_bsr_pos = nullptr;     // [fragment][4] (box - boxlo[chunk]) << 8 | column % kBsrBX
+    int* d_bsr_rbptr = nullptr;   // [nrb + 1]
+    int* d_bsr_hi = nullptr;      // [nch] boxes of kBsrBX nodes resident once chunk c (4 row blocks) is staged
+    int* d_bsr_lo = nullptr;      // [nch] lowest box still needed from chunk c on
+    int bsr_nbox[4] = {0, 0, 0, 0};  // ring size (boxes) that allows d chunks of lookahead, d = 0..3
+    int bsr_maxf = 0;
+    int64_t bsr_frags = 0;
     // advection bundles
     const sbp_op* inner = nullptr;
     double* d_b = nullptr;
@@ -91,6 +101,7 @@ struct sbp_op {
     double* d_bnd_tau = nullptr;
     double* d_a = nullptr;
     double* d_q_consts = nullptr;  // per-node constants for the analysis quantities
+    int* d_rbmask = nullptr;       // 2D bundle over a block-sparse operator: inflow rows of every 8-row block (bit mask)
     double sat_a0 = 1.0, sat_aN = 1.0, sat_w0 = 1.0, sat_wN = 1.0;  // 1D bundle: end speeds and end weights
 };
 
@@ -140,6 +151,10 @@ int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const doub
                           double beta);
 int32_t launch_sparse(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                       double beta, const sbp_op* adv, const double* g, int64_t g_stride, double* quantities);
+bool bsr_available(const sbp_ctx* ctx, const sbp_op* op);
+bool bsr_can_run(const sbp_op* op, const double* U);
+int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
+                   const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat);
 int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V, int64_t B,
                          int mode, double* out, double* out_sum);
 int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t B, double factor, int inverse);

@@ -5,6 +5,8 @@ Tolerance (north_star): Float64, per instance  max_i |y_gpu - y_ref| / max_i |y_
 The summation order differs from OpenBLAS, so bitwise equality is not expected; the extended-precision truth
 is used to show the GPU error is of the size of the reference BLAS's own rounding error.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -212,20 +214,62 @@ def test_apply_large_dense(ctx, N, B):
 
 
 # ---- K2: structurally sparse operators ---------------------------------------------------------------------------
-@pytest.mark.parametrize("order,N", [(2, 101), (4, 101), (4, 400), (2, 1500)])
+@pytest.fixture(params=["bsr", "sell"])
+def sparse_kernel(request, monkeypatch):
+    """both sparse kernels: block-sparse DMMA (bsr.cu, default) and the scalar row-blocked SELL kernel (sparse.cu);
+    SBP_SPARSE_KERNEL is read by sbp_op_sparse_create at every upload"""
+    monkeypatch.setenv("SBP_SPARSE_KERNEL", request.param)
+    return {"bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
+
+
+@pytest.mark.parametrize("order,N", [(2, 101), (4, 101), (4, 102), (4, 400), (2, 1500)])
 @pytest.mark.parametrize("B", [1, 19, 1030])
-def test_apply_sparse_1d(ctx, order, N, B):
+def test_apply_sparse_1d(ctx, order, N, B, sparse_kernel):
     D = S.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
     D.storage = "sparse"
     Do = O.mattsson_nordstrom_2004(order, 0.0, 1.0, N)
     U = rand_batch(B, N, 3)
     du = D * ctx.upload(U)
-    assert D.device_op(ctx).info()["kernel"] == "csr_smem"
+    # the tensor-core kernel streams the batch with TMA tensor copies: rows must be 16-byte multiples (N even)
+    assert D.device_op(ctx).info()["kernel"] == (sparse_kernel if N % 2 == 0 else "csr_smem")
     assert rel_err(du.to_host(), O.apply_batch(Do.matrix(), U)) <= TOL
     Y0 = rand_batch(B, N, 4)
     dv = ctx.upload(Y0)
     S.mul_(dv, D, ctx.upload(U), 0.5, -2.0)
     assert rel_err(dv.to_host(), O.apply_batch(Do.matrix(), U, 0.5, -2.0, Y0)) <= TOL
+
+
+@pytest.mark.parametrize("N,nnz_row,B", [(8, 3, 5), (37, 6, 129), (250, 9, 77), (1000, 12, 300), (1001, 12, 300),
+                                         (4000, 10, 41),
+                                         (30000, 5, 9)])
+def test_apply_sparse_general_csr(ctx, N, nnz_row, B, sparse_kernel):
+    """arbitrary CSR patterns (no band structure => the node ring holds the whole vector), duplicated entries that must
+    accumulate, empty rows, a wrap-around row, odd N / N % 8 != 0, beta != 0; N = 30000 exceeds shared memory and must
+    take the global-gather kernel"""
+    rng = np.random.default_rng(N)
+    rowptr, col, val = [0], [], []
+    for i in range(N):
+        k = 0 if i % 11 == 3 else int(rng.integers(1, 2 * nnz_row))
+        c = rng.integers(0, N, size=k)
+        if k and i % 5 == 0:
+            c[-1] = c[0]  # duplicate column in the same row
+        col.extend(c.tolist())
+        val.extend(rng.normal(size=k).tolist())
+        rowptr.append(len(col))
+    import scipy.sparse as sp
+
+    M = sp.csr_matrix((np.array(val), np.array(col, dtype=np.int32), np.array(rowptr, dtype=np.int32)), shape=(N, N))
+    M.sum_duplicates()
+    op = S.upload_csr(ctx, N, np.array(rowptr, np.int32), np.array(col, np.int32), np.array(val), None, 0.75)
+    # the tensor-core kernel needs one 8-instance tile (8 N doubles + two chunks of fragments) in shared memory
+    assert op.info()["kernel"] == (sparse_kernel if N <= 1001 and N % 2 == 0 else "csr_smem")
+    U, Y0 = rand_batch(B, N, 1), rand_batch(B, N, 2)
+    u, y = ctx.upload(U), ctx.upload(Y0)
+    S._lib.check(ctx._lib.sbp_apply(ctx.handle, op.handle, C.c_void_p(y.ptr), C.c_void_p(u.ptr), B, 2.0, -0.5))
+    ref = 2.0 * 0.75 * (M @ U.T).T - 0.5 * Y0
+    # rows may cancel to ~0: bound by the magnitude of the summed terms
+    mag = 1.5 * (abs(M) @ np.abs(U).T).T + 0.5 * np.abs(Y0)
+    assert np.max(np.abs(y.to_host() - ref) / np.maximum(mag, 1e-300).max(axis=1, keepdims=True)) <= TOL
 
 
 def test_sparse_equals_dense_path(ctx):
@@ -270,7 +314,7 @@ def _oracle_md(D):
 
 @pytest.mark.parametrize("storage", ["sparse", "dense"])
 @pytest.mark.parametrize("n1", [6, 12, 20])
-def test_apply_mfsbp_directions(ctx, n1, storage):
+def test_apply_mfsbp_directions(ctx, n1, storage, sparse_kernel):
     D = _scattered_mfsbp(n1)
     D.storage = storage
     for d in D._dirs:
@@ -284,7 +328,7 @@ def test_apply_mfsbp_directions(ctx, n1, storage):
 # ---- K3: fused 2D advection RHS with SAT + analysis quantities -------------------------------------------------
 @pytest.mark.parametrize("storage", ["sparse", "dense"])
 @pytest.mark.parametrize("a", [(1.0, 1.0), (1.0, -0.5), (-0.3, 0.0)])
-def test_rhs_advection2d(ctx, storage, a):
+def test_rhs_advection2d(ctx, storage, a, sparse_kernel):
     D = _scattered_mfsbp(12, seed=1)
     u0 = lambda x: np.exp(-30 * (x[0] ** 2 + x[1] ** 2))
     g = lambda x, t: u0((x[0] - a[0] * t, x[1] - a[1] * t)) + 0.1 * np.sin(3 * x[0] - x[1] + t)
@@ -311,7 +355,7 @@ def test_rhs_advection2d(ctx, storage, a):
     assert np.max(np.abs(Q - qref) / mag) <= 1e-12
 
 
-def test_rhs_advection2d_per_instance_boundary_data(ctx):
+def test_rhs_advection2d_per_instance_boundary_data(ctx, sparse_kernel):
     D = _scattered_mfsbp(8, seed=2)
     a = (0.7, 1.0)
     semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, lambda x, t: 0.0, storage="sparse")
@@ -329,7 +373,7 @@ def test_rhs_advection2d_per_instance_boundary_data(ctx):
 # ---- 1D advection (config 1) --------------------------------------------------------------------------------------
 @pytest.mark.parametrize("storage", ["sparse", "dense"])
 @pytest.mark.parametrize("speed", ["unit", "variable", "negative"])
-def test_rhs_advection1d(ctx, storage, speed):
+def test_rhs_advection1d(ctx, storage, speed, sparse_kernel):
     N = 101
     D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
     D.storage = storage
@@ -354,7 +398,7 @@ def test_rhs_advection1d(ctx, storage, speed):
     assert np.max(np.abs(Q - qref) / mag) <= 1e-12
 
 
-def test_ssprk53_example_run(ctx):
+def test_ssprk53_example_run(ctx, sparse_kernel):
     """examples/RBF_FSBP_advection.jl:9-51 with a closed-form banded SBP operator standing in for the RBF operator:
     N = 101, a = 1, u0 = tanh(50(x-0.1)), SSPRK53, dt = 0.009, tspan = (0, 0.5), AnalysisCallback(dt = 0.01)."""
     N = 101
