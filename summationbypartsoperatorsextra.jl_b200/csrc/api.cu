@@ -1,6 +1,7 @@
 // api.cu -- extern "C" entry points of libsbp_b200.so (see include/sbp_b200.h for the contract and the
 // reference file:line each entry point replaces).
 #include <algorithm>
+#include <iterator>
 #include <cmath>
 #include <cstring>
 #include <dlfcn.h>
@@ -308,25 +309,95 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
     return upload(&op->d_sell_val, v);
 }
 
-// Block-sparse DMMA image (bsr.cu): row blocks of 8 rows; the sorted union of a block's columns is cut into fragments
-// of 4 columns (the last one padded with a repeated column and zero values).  Chunks of 4 row blocks define the node
-// window [lo_c, hi_c) that must be resident while the chunk is multiplied; W[d] is the ring size that lets the nodes of
-// the next d chunks stream in while a chunk is being consumed (the stream continues across the tiles of a CTA with a
-// period of Np = N rounded up to even, plus a gap of two slots).
+// Block-sparse DMMA image (bsr.cu).
+//  * ROW BLOCKS of 8 rows = two QUADS of 4 consecutive rows (aligned to 4).  The second quad is chosen greedily among
+//    the quads that share columns with the first one so that the union of the block's columns is smallest: for a
+//    stencil-like operator on a 2-D cloud a 2 x 4 patch of nodes needs ~25% fewer fragments than 8 rows in a line; for
+//    banded 1-D operators the partner is simply the next quad.  A lane of the C fragment owns an aligned row pair, so
+//    the output is still written with 16-byte stores.
+//  * FRAGMENTS: the union of a block's columns, 4 columns each (see the bank-conflict note below).
+//  * CHUNKS of 4 row blocks define the window of TMA boxes (kBsrBX nodes) [blo_c, bhi_c) that must be resident while
+//    the chunk is multiplied; nbox[d] is the ring size that lets the boxes of the next d chunks stream in meanwhile
+//    (the stream continues across the tiles of a CTA, nbt boxes per tile).
 static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, const std::vector<int>& col,
                          const std::vector<double>& val) {
     constexpr int CH = 4;  // == kBsrCH
-    const int nrb = (N + 7) / 8, nch = (nrb + CH - 1) / CH;
-    std::vector<int> rbptr(nrb + 1, 0), pos;
-    std::vector<double> frag;
-    std::vector<int> cmin(nch, N), cmax(nch, 0);
-    for (int rb = 0; rb < nrb; rb++) {
-        std::vector<int> u;
-        const int r_end = std::min(N, rb * 8 + 8);
-        for (int r = rb * 8; r < r_end; r++)
+    constexpr int BX = kBsrBX;
+    const int nq = (N + 3) / 4;
+    auto union_of = [&](int q, std::vector<int>& u) {
+        for (int r = 4 * q; r < std::min(N, 4 * q + 4); r++)
             for (int j = rowptr[r]; j < rowptr[r + 1]; j++) u.push_back(col[j]);
+    };
+    auto uniq = [](std::vector<int>& u) {
         std::sort(u.begin(), u.end());
         u.erase(std::unique(u.begin(), u.end()), u.end());
+    };
+    std::vector<std::vector<int>> qcols(nq);
+    for (int q = 0; q < nq; q++) {
+        union_of(q, qcols[q]);
+        uniq(qcols[q]);
+    }
+    // greedy pairing of quads
+    std::vector<char> used(nq, 0);
+    std::vector<int> rows;  // 2 per block: first row of quad A, first row of quad B (or >= N: none)
+    const int none = 4 * nq + 4;
+    const bool pair_far = getenv("SBP_BSR_NO_PAIRING") == nullptr;
+    for (int qa = 0; qa < nq; qa++) {
+        if (used[qa]) continue;
+        used[qa] = 1;
+        int best = -1;
+        size_t best_size = ~size_t(0);
+        std::vector<int> cand;
+        if (pair_far)
+            for (int cidx : qcols[qa]) cand.push_back(cidx / 4);
+        if (qa + 1 < nq) cand.push_back(qa + 1);
+        uniq(cand);
+        std::vector<int> merged;
+        for (int qb : cand) {
+            if (used[qb]) continue;
+            merged.clear();
+            std::set_union(qcols[qa].begin(), qcols[qa].end(), qcols[qb].begin(), qcols[qb].end(),
+                           std::back_inserter(merged));
+            const size_t sz = (merged.size() + 3) / 4;  // fragments
+            if (sz < best_size || (sz == best_size && std::abs(qb - qa) < std::abs(best - qa))) {
+                best_size = sz;
+                best = qb;
+            }
+        }
+        if (best < 0)  // no unassigned neighbour: take the next free quad so that blocks stay full
+            for (int qb = qa + 1; qb < nq; qb++)
+                if (!used[qb]) {
+                    best = qb;
+                    break;
+                }
+        rows.push_back(4 * qa);
+        if (best >= 0) {
+            used[best] = 1;
+            rows.push_back(4 * best);
+        } else {
+            rows.push_back(none);
+        }
+    }
+    const int nrb = (int)rows.size() / 2, nch = (nrb + CH - 1) / CH;
+    auto block_row = [&](int rb, int g) { return (g < 4 ? rows[2 * rb] : rows[2 * rb + 1] - 4) + g; };
+    std::vector<int> rbf(nrb + 1, 0), pos;
+    std::vector<double> frag;
+    std::vector<int> cmin(nch, N), cmax(nch, 0);
+    op->bsr_rb_first = op->bsr_rb_last = 0;
+    for (int rb = 0; rb < nrb; rb++) {
+        std::vector<int> u;
+        const int c = rb / CH;
+        for (int g = 0; g < 8; g++) {
+            const int r = block_row(rb, g);
+            if (r >= N) continue;
+            if (r == 0) op->bsr_rb_first = rb;
+            if (r == N - 1) op->bsr_rb_last = rb;
+            for (int j = rowptr[r]; j < rowptr[r + 1]; j++) u.push_back(col[j]);
+            // the block's own rows are part of the chunk's window (the SAT epilogues read u_j from the ring)
+            cmin[c] = std::min(cmin[c], r);
+            cmax[c] = std::max(cmax[c], r + 1);
+        }
+        uniq(u);
         // Fragments of 4 columns.  The A-operand gather of a fragment is bank-conflict free iff its 4 columns differ
         // mod 4 (rows of a box are 36 = 4 (mod 16) doubles apart), so columns are dealt from 4 residue buckets, the
         // fullest first; a fragment short of columns repeats one of its own (same address => broadcast, value 0).
@@ -341,11 +412,10 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
             for (int f = 0; f < nf; f++) {
                 int taken = 0, cols[4];
                 int order[4] = {0, 1, 2, 3};
-                std::sort(order, order + 4, [&](int a, int b) { return bucket[a].size() > bucket[b].size(); });
-                for (int pass = 0; pass < 4 && taken < 4; pass++)
+                std::sort(order, order + 4, [&](int x, int y) { return bucket[x].size() > bucket[y].size(); });
+                for (int pass = 0; pass < 4 && taken < 4; pass++)  // later passes: fewer than 4 residue classes left
                     for (int q = 0; q < 4 && taken < 4; q++) {
                         std::vector<int>& bk = bucket[order[q]];
-                        // later passes only run when fewer than 4 residue classes are left
                         if (!bk.empty()) {
                             cols[taken++] = bk.back();
                             bk.pop_back();
@@ -358,24 +428,22 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
                 }
             }
         }
-        for (int r = rb * 8; r < r_end; r++)
+        for (int g = 0; g < 8; g++) {
+            const int r = block_row(rb, g);
+            if (r >= N) continue;
             for (int j = rowptr[r]; j < rowptr[r + 1]; j++) {
                 const int k = (int)(std::lower_bound(u.begin(), u.end(), col[j]) - u.begin());
                 const int w = where[k];
-                frag[(f0 + w / 4) * 32 + (size_t)(r - rb * 8) * 4 + (w & 3)] += val[j];  // lane = 4*g + t
+                frag[(f0 + w / 4) * 32 + (size_t)g * 4 + (w & 3)] += val[j];  // lane = 4*g + t; duplicates accumulate
             }
-        rbptr[rb + 1] = (int)(f0 + nf);
-        const int c = rb / CH;
-        // the chunk's own rows are part of its window (the SAT epilogues read u_j from the ring)
-        cmin[c] = std::min(cmin[c], rb * 8);
-        cmax[c] = std::max(cmax[c], r_end);
+        }
+        rbf[rb + 1] = (int)(f0 + nf);
         if (!u.empty()) {
             cmin[c] = std::min(cmin[c], u.front());
             cmax[c] = std::max(cmax[c], u.back() + 1);
         }
     }
-    // windows in units of TMA boxes (kBsrBX nodes): boxes [0, bhi[c]) resident for chunk c, none below blo[c] needed later
-    constexpr int BX = kBsrBX;
+    // windows in units of TMA boxes: boxes [0, bhi[c]) resident for chunk c, none below blo[c] needed later
     std::vector<int> blo(nch), bhi(nch);
     for (int c = 0, m = 0; c < nch; c++) {
         m = std::max(m, cmax[c]);
@@ -386,7 +454,7 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
         blo[c] = m / BX;
     }
     for (int rb = 0; rb < nrb; rb++)
-        for (int f = rbptr[rb] * 4; f < rbptr[rb + 1] * 4; f++) {
+        for (int f = rbf[rb] * 4; f < rbf[rb + 1] * 4; f++) {
             const int n = pos[f];
             pos[f] = ((n / BX - blo[rb / CH]) << 8) | (n % BX);
         }
@@ -394,7 +462,18 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     // overwrite slots that no item >= s - d still needs
     const int nbt = (N + BX - 1) / BX;
     int maxf = 1;
-    for (int c = 0; c < nch; c++) maxf = std::max(maxf, rbptr[std::min(nrb, c * CH + CH)] - rbptr[c * CH]);
+    std::vector<int> rbmeta(4 * (size_t)nrb), chmeta(4 * (size_t)nch);
+    for (int c = 0; c < nch; c++) {
+        const int fa = rbf[c * CH], fb = rbf[std::min(nrb, c * CH + CH)];
+        maxf = std::max(maxf, fb - fa);
+        chmeta[4 * c + 0] = fa, chmeta[4 * c + 1] = fb, chmeta[4 * c + 2] = blo[c], chmeta[4 * c + 3] = bhi[c];
+    }
+    for (int rb = 0; rb < nrb; rb++) {
+        rbmeta[4 * rb + 0] = rbf[rb] - rbf[(rb / CH) * CH];
+        rbmeta[4 * rb + 1] = rbf[rb + 1] - rbf[rb];
+        rbmeta[4 * rb + 2] = rows[2 * rb];
+        rbmeta[4 * rb + 3] = rows[2 * rb + 1];
+    }
     for (int d = 0; d < 4; d++) {
         long long need = 1;
         const int items = nch * (d + 2);
@@ -407,6 +486,8 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
         op->bsr_nbox[d] = (int)need;
     }
     op->bsr_maxf = maxf;
+    op->bsr_nrb = nrb;
+    op->bsr_rows = rows;
     op->bsr_frags = (int64_t)frag.size() / 32;
     if (frag.empty()) {
         frag.assign(32, 0.0);
@@ -414,9 +495,8 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     }
     int32_t rc = upload(&op->d_bsr_val, frag);
     if (!rc) rc = upload(&op->d_bsr_pos, pos);
-    if (!rc) rc = upload(&op->d_bsr_rbptr, rbptr);
-    if (!rc) rc = upload(&op->d_bsr_hi, bhi);
-    if (!rc) rc = upload(&op->d_bsr_lo, blo);
+    if (!rc) rc = upload(&op->d_bsr_rbmeta, rbmeta);
+    if (!rc) rc = upload(&op->d_bsr_chmeta, chmeta);
     return rc;
 }
 
@@ -608,8 +688,8 @@ int32_t sbp_op_destroy(sbp_op* op) {
     void* ptrs[] = {op->d_D,         op->d_frag,     op->d_wfrag,    op->d_w,        op->d_frag_sym, op->d_rowptr,
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
-                    op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbptr, op->d_bsr_hi,
-                    op->d_rbmask,    op->d_bsr_lo};
+                    op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
+                    op->d_rbmask};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -732,9 +812,12 @@ int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h
     int32_t rc = upload(&op->d_b, b);
     if (!rc) rc = upload(&op->d_mode, mode);
     if (!rc && A->variant == SBP_KERNEL_BSR_DMMA) {
-        std::vector<int> rbmask((N + 7) / 8, 0);
-        for (int i = 0; i < N; i++)
-            if (h_mode[i] == 1) rbmask[i >> 3] |= 1 << (i & 7);
+        std::vector<int> rbmask(A->bsr_nrb, 0);  // bit r <=> row r of the block (quad A rows 0..3, quad B rows 4..7)
+        for (int rb = 0; rb < A->bsr_nrb; rb++)
+            for (int r = 0; r < 8; r++) {
+                const int i = (r < 4 ? A->bsr_rows[2 * rb] : A->bsr_rows[2 * rb + 1] - 4) + r;
+                if (i < N && h_mode[i] == 1) rbmask[rb] |= 1 << r;
+            }
         rc = upload(&op->d_rbmask, rbmask);
     }
     if (!rc) rc = upload(&op->d_q_consts, qc);

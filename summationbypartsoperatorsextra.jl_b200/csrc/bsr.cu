@@ -45,14 +45,15 @@ struct BsrParams {
     double* __restrict__ dU;
     const double* __restrict__ val;   // [fragment][32]
     const int* __restrict__ pos;      // [fragment][4]  (box - boxlo[chunk]) << 8 | node % kBsrBX
-    const int* __restrict__ rbptr;    // [nrb + 1] fragments per row block (prefix sum)
-    const int* __restrict__ boxhi;    // [nch] boxes [0, boxhi[c]) of the tile are resident once chunk c has been staged
-    const int* __restrict__ boxlo;    // [nch] no chunk >= c touches a box below boxlo[c]
+    const int4* __restrict__ rbmeta;  // [nrb] {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
+    const int4* __restrict__ chmeta;  // [nch] {first fragment, end fragment, boxlo, boxhi}: boxes [0, boxhi) of the tile are
+                                      // resident once the chunk has been staged; no later chunk touches a box below boxlo
     int N, nrb, nch, nbox, nbt, maxf, nst;  // nbox ring slots, nbt boxes per tile, nst pipeline stages
+    int rb_first, rb_last;            // row blocks holding row 0 and row N-1 (1D SATs)
     long long B;
     double alpha, beta;
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
-    const int* __restrict__ rbmask;   // [nrb] bit r set <=> row 8rb+r is an inflow node
+    const int* __restrict__ rbmask;   // [nrb] bit r set <=> row r of the block is an inflow node
     const double* __restrict__ bdiag;
     const double* __restrict__ g;
     long long g_stride;
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
             mbar_init(&bar_full[s], 1);              // the producer's arrive.expect_tx
-            mbar_init(&bar_empty[s], kBsrCH * MH);   // lane 0 of the consumer warps of a group
+            mbar_init(&bar_empty[s], CONS);          // lane 0 of every consumer warp
         }
         mbar_fence_init();
     }
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
                 int jb = 0;  // boxes of this tile already requested
                 for (int c = 0; c < p.nch; c++) {
                     if (round > 0) mbar_wait(&bar_empty[st], (round - 1) & 1);
-                    const int jn = __ldg(p.boxhi + c);
-                    const int f0 = __ldg(p.rbptr + c * kBsrCH), f1 = __ldg(p.rbptr + min((c + 1) * kBsrCH, p.nrb));
+                    const int4 cm = __ldg(p.chmeta + c);
+                    const int jn = cm.w, f0 = cm.x, f1 = cm.y;
                     const unsigned vbytes = (unsigned)(f1 - f0) * 256u, pbytes = (unsigned)(f1 - f0) * 16u;
                     mbar_arrive_expect_tx(&bar_full[st], (unsigned)(jn - jb) * (unsigned)(BOX * 8) + vbytes + pbytes);
                     for (int j = jb; j < jn; j++) {
@@ -132,115 +133,150 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
     const int grp = warp / (kBsrCH * MH), slotw = (warp / MH) % kBsrCH, mh = warp % MH;
     const int i0 = mh * 8 * MTW;  // first instance (tile row) of this warp
     const double* su = s_u + (i0 + g) * BX;
-    int item = 0, st = 0, round = 0, off = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+
+    // per-item operator constants (independent of the tile): fetched one item ahead so that their L2 latency is hidden
+    struct Meta {
+        int frel, nf, r0, blo, mask;
+        double sb0, sb1;
+        bool active;
+    };
+    auto load_meta = [&](int c) {
+        Meta m;
+        const int rb = c * kBsrCH + slotw;
+        m.active = rb < p.nrb;
+        m.frel = m.nf = m.blo = m.mask = 0;
+        m.r0 = N;
+        m.sb0 = m.sb1 = 0.0;
+        if (m.active) {
+            const int4 r = __ldg(p.rbmeta + rb);
+            m.frel = r.x, m.nf = r.y;
+            m.r0 = (t < 2 ? r.z : r.w - 4) + 2 * t;  // lane owns rows r0, r0 + 1 (pair t of the block)
+            m.blo = __ldg(p.chmeta + c).z;
+            if (SAT == 1) {
+                m.mask = (__ldg(p.rbmask + rb) >> (2 * t)) & 3;
+                if (m.mask & 1) m.sb0 = __ldg(p.bdiag + m.r0);
+                if (m.mask & 2) m.sb1 = __ldg(p.bdiag + m.r0 + 1);
+            }
+        }
+        return m;
+    };
+
+    // The CTA's stream of items = (tile, chunk) pairs.  Item i is multiplied by group i % G; EVERY consumer warp passes
+    // every item's "full" barrier in order and arrives on its "empty" barrier: a chunk also reads boxes that were
+    // requested together with earlier items (of the other group), so their arrival must have been observed too, and
+    // a stage may only be refilled once no warp can still be waiting on its previous phase.
+    int c = 0, off = 0, st = 0, round = 0, turn = 0;
+    long long tile = blockIdx.x;
+    Meta m = load_meta(grp % p.nch);
+    auto next_item = [&]() {
+        if (++c == p.nch) {
+            c = 0;
+            tile += gridDim.x;
+            off += stepb;
+            if (off >= nbox) off -= nbox;
+        }
+        if (++st == nst) st = 0, round++;
+        if (++turn == kBsrGroups) turn = 0;
+    };
+    for (; tile < ntiles; next_item()) {
+        if (turn != grp) {
+            mbar_wait(&bar_full[st], round & 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[st]);
+            continue;
+        }
+        int cn = c + kBsrGroups;  // chunk of this warp's next item: its operator constants are prefetched now
+        while (cn >= p.nch) cn -= p.nch;
+        const Meta mn = load_meta(cn);
+
         const long long b0 = tile * TI;
         const int nb = (p.B - b0) < TI ? (int)(p.B - b0) : TI;
-        for (int c = 0; c < p.nch; c++, item++) {
-            const int my_st = st, my_round = round;
-            if (++st == nst) st = 0, round++;
-            if (item % kBsrGroups != grp) continue;
-            const int rb = c * kBsrCH + slotw;
-            const bool active = rb < p.nrb;
-            const int r0 = 8 * rb + 2 * t;
-            // operator-independent epilogue inputs are requested before the wait so that their latency is hidden
-            int f0 = 0, nf = 0, blo = 0, mask = 0;
-            double sb0 = 0.0, sb1 = 0.0;
-            if (active) {
-                const int fbase = __ldg(p.rbptr + c * kBsrCH);
-                f0 = __ldg(p.rbptr + rb) - fbase;
-                nf = __ldg(p.rbptr + rb + 1) - fbase - f0;
-                blo = __ldg(p.boxlo + c);
-                if (SAT == 1) {
-                    mask = (__ldg(p.rbmask + rb) >> (2 * t)) & 3;
-                    if (mask & 1) sb0 = __ldg(p.bdiag + r0);
-                    if (mask & 2) sb1 = __ldg(p.bdiag + r0 + 1);
-                }
-            }
-            int cb = blo % nbox + off;  // ring slot of box blo in this tile
-            if (cb >= nbox) cb -= nbox;
-            // element offset of (box-relative, column) code q inside the ring
-            auto ring_off = [&](int q) {
-                int sb = cb + (q >> 8);
-                if (sb >= nbox) sb -= nbox;
-                return sb * BOX + (q & 255);
-            };
-            double acc[MT][2];
+        const int rb = c * kBsrCH + slotw;
+        const int r0 = m.r0, blo = m.blo, mask = m.mask, nf = m.nf;
+        int cb = blo % nbox + off;  // ring slot of box blo in this tile
+        if (cb >= nbox) cb -= nbox;
+        // element offset of (box-relative, column) code q inside the ring
+        auto ring_off = [&](int q) {
+            int sb = cb + (q >> 8);
+            if (sb >= nbox) sb -= nbox;
+            return sb * BOX + (q & 255);
+        };
+        double acc[MT][2];
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
-            double u0[MT], u1[MT];  // SAT == 1: own-row values; SAT == 2: the finished SAT terms of rows r0, r0 + 1
+        for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
+        double u0[MT], u1[MT];  // SAT == 1: own-row values; SAT == 2: the finished SAT terms of rows r0, r0 + 1
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) u0[mt] = u1[mt] = 0.0;
+        for (int mt = 0; mt < MT; mt++) u0[mt] = u1[mt] = 0.0;
 
-            mbar_wait(&bar_full[my_st], my_round & 1);
-            if (active) {
-                const double* sv = s_val + (size_t)my_st * p.maxf * 32 + (size_t)f0 * 32 + lane;
-                const int* sp = s_pos + (size_t)my_st * p.maxf * 4 + f0 * 4 + t;
-                if (nf > 0) {
-                    // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
-                    double b_cur = sv[0], a_cur[MT];
-                    {
-                        const int o0 = ring_off(sp[0]);
+        mbar_wait(&bar_full[st], round & 1);
+        if (m.active) {
+            const double* sv = s_val + (size_t)st * p.maxf * 32 + (size_t)m.frel * 32 + lane;
+            const int* sp = s_pos + (size_t)st * p.maxf * 4 + m.frel * 4 + t;
+            if (nf > 0) {
+                // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
+                double b_cur = sv[0], a_cur[MT];
+                {
+                    const int o0 = ring_off(sp[0]);
 #pragma unroll
-                        for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * 8 * BX + o0];
-                    }
-                    int o_nxt = ring_off(sp[nf > 1 ? 4 : 0]);
-                    for (int f = 1; f < nf; f++) {
-                        const double b_nxt = sv[f * 32];
-                        double a_nxt[MT];
+                    for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * 8 * BX + o0];
+                }
+                int o_nxt = ring_off(sp[nf > 1 ? 4 : 0]);
+                for (int f = 1; f < nf; f++) {
+                    const double b_nxt = sv[f * 32];
+                    double a_nxt[MT];
 #pragma unroll
-                        for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * 8 * BX + o_nxt];
-                        o_nxt = ring_off(sp[(f + 1 < nf ? f + 1 : f) * 4]);
-#pragma unroll
-                        for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
-                        b_cur = b_nxt;
-#pragma unroll
-                        for (int mt = 0; mt < MT; mt++) a_cur[mt] = a_nxt[mt];
-                    }
+                    for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * 8 * BX + o_nxt];
+                    o_nxt = ring_off(sp[(f + 1 < nf ? f + 1 : f) * 4]);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
+                    b_cur = b_nxt;
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) a_cur[mt] = a_nxt[mt];
                 }
-                if (SAT == 1 && mask) {  // own-row values (the chunk's own rows are inside its window)
-                    const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
-                    const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
-                    const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        u0[mt] = su[mt * 8 * BX + o0];
-                        u1[mt] = su[mt * 8 * BX + o1];
-                    }
-                }
-                if (SAT == 2 && (rb == 0 || rb == p.nrb - 1)) {
-                    // 1D SATs at rows 0 and N-1: one division per instance.  Lane l evaluates them for the warp's
-                    // instances l (and l + 32) in parallel; the owners of the two rows fetch them by shuffle.
-                    const int qL = 0, qR = (N - 1) / BX;
-                    const int oL = ring_off(((qL - blo) << 8) | 0), oR = ring_off(((qR - blo) << 8) | (N - 1 - qR * BX));
-                    double sl[(8 * MTW + 31) / 32], sr[(8 * MTW + 31) / 32];
+                for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
+            }
+            if (SAT == 1 && mask) {  // own-row values (the chunk's own rows are inside its window)
+                const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
+                const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
+                const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
 #pragma unroll
-                    for (int k = 0; k < (8 * MTW + 31) / 32; k++) {
-                        const int il = lane + 32 * k;  // instance within the warp's share
-                        sl[k] = sr[k] = 0.0;
-                        if (il < 8 * MTW && i0 + il < nb) {
-                            const long long inst = b0 + i0 + il;
-                            const double* up = s_u + (size_t)(i0 + il) * BX;
-                            if (rb == 0) sl[k] = sat1d_left(p.sat, inst, p.sat.a0 * up[oL]);
-                            if (rb == p.nrb - 1) sr[k] = sat1d_right(p.sat, inst, p.sat.aN * up[oR]);
-                        }
-                    }
-#pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        const int il = mt * 8 + g;
-                        const double vl = __shfl_sync(0xffffffffu, sl[il >> 5], il & 31);
-                        const double vr = __shfl_sync(0xffffffffu, sr[il >> 5], il & 31);
-                        if (r0 == 0) u0[mt] = vl;
-                        if (r0 == N - 1) u0[mt] += vr;
-                        if (r0 + 1 == N - 1) u1[mt] = vr;
-                    }
+                for (int mt = 0; mt < MT; mt++) {
+                    u0[mt] = su[mt * 8 * BX + o0];
+                    u1[mt] = su[mt * 8 * BX + o1];
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[my_st]);  // the stage (and the ring slots behind it) may be refilled
-            if (!active) continue;
+            if (SAT == 2 && (rb == p.rb_first || rb == p.rb_last)) {
+                // 1D SATs at rows 0 and N-1: one division per instance.  Lane l evaluates them for the warp's
+                // instances l (and l + 32) in parallel; the owners of the two rows fetch them by shuffle.
+                const int qR = (N - 1) / BX;
+                const int oL = ring_off((0 - blo) << 8), oR = ring_off(((qR - blo) << 8) | (N - 1 - qR * BX));
+                double sl[(8 * MTW + 31) / 32], sr[(8 * MTW + 31) / 32];
+#pragma unroll
+                for (int k = 0; k < (8 * MTW + 31) / 32; k++) {
+                    const int il = lane + 32 * k;  // instance within the warp's share
+                    sl[k] = sr[k] = 0.0;
+                    if (il < 8 * MTW && i0 + il < nb) {
+                        const long long inst = b0 + i0 + il;
+                        const double* up = s_u + (size_t)(i0 + il) * BX;
+                        if (rb == p.rb_first) sl[k] = sat1d_left(p.sat, inst, p.sat.a0 * up[oL]);
+                        if (rb == p.rb_last) sr[k] = sat1d_right(p.sat, inst, p.sat.aN * up[oR]);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const int il = mt * 8 + g;
+                    const double vl = __shfl_sync(0xffffffffu, sl[il >> 5], il & 31);
+                    const double vr = __shfl_sync(0xffffffffu, sr[il >> 5], il & 31);
+                    if (r0 == 0) u0[mt] = vl;
+                    if (r0 == N - 1) u0[mt] += vr;
+                    if (r0 + 1 == N - 1) u1[mt] = vr;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);  // the stage (and the ring slots behind it) may be refilled
+        if (m.active) {
             // ---- epilogue: lane owns rows r0, r0+1 of instance i0 + 8mt + g ----
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
@@ -250,8 +286,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
                 double y0 = p.alpha * acc[mt][0], y1 = p.alpha * acc[mt][1];
                 if (SAT == 1 && mask) {
                     const double* gp = p.g + inst * p.g_stride + r0;
-                    if (mask & 1) y0 += sb0 * (u0[mt] - __ldg(gp));
-                    if (mask & 2) y1 += sb1 * (u1[mt] - __ldg(gp + 1));
+                    if (mask & 1) y0 += m.sb0 * (u0[mt] - __ldg(gp));
+                    if (mask & 2) y1 += m.sb1 * (u1[mt] - __ldg(gp + 1));
                 }
                 if (SAT == 2) {
                     y0 += u0[mt];
@@ -279,8 +315,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
                 }
             }
         }
-        off += stepb;
-        if (off >= nbox) off -= nbox;
+        m = mn;
     }
 }
 
@@ -361,12 +396,13 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.dU = dU;
     p.val = op->d_bsr_val;
     p.pos = op->d_bsr_pos;
-    p.rbptr = op->d_bsr_rbptr;
-    p.boxhi = op->d_bsr_hi;
-    p.boxlo = op->d_bsr_lo;
+    p.rbmeta = reinterpret_cast<const int4*>(op->d_bsr_rbmeta);
+    p.chmeta = reinterpret_cast<const int4*>(op->d_bsr_chmeta);
     p.N = op->N;
-    p.nrb = (op->N + 7) / 8;
+    p.nrb = op->bsr_nrb;
     p.nch = (p.nrb + kBsrCH - 1) / kBsrCH;
+    p.rb_first = op->bsr_rb_first;
+    p.rb_last = op->bsr_rb_last;
     p.nbt = (op->N + kBsrBX - 1) / kBsrBX;
     p.maxf = op->bsr_maxf;
     p.B = B;

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/sbp_b200.h"
 
@@ -86,9 +87,10 @@ struct sbp_op {
     // sparse, block-sparse DMMA image (bsr.cu): row blocks of 8 rows, fragments of 4 gathered columns
     double* d_bsr_val = nullptr;  // [fragment][32] B-operand fragments (row g, column t)
     int* d_bsr_pos = nullptr;     // [fragment][4] (box - boxlo[chunk]) << 8 | column % kBsrBX
-    int* d_bsr_rbptr = nullptr;   // [nrb + 1]
-    int* d_bsr_hi = nullptr;      // [nch] boxes of kBsrBX nodes resident once chunk c (4 row blocks) is staged
-    int* d_bsr_lo = nullptr;      // [nch] lowest box still needed from chunk c on
+    int* d_bsr_rbmeta = nullptr;  // [nrb][4] {first fragment relative to its chunk, fragments, first row of quad A, of quad B}
+    int* d_bsr_chmeta = nullptr;  // [nch][4] {first fragment, end fragment, lowest box still needed, boxes resident}
+    int bsr_nrb = 0, bsr_rb_first = 0, bsr_rb_last = 0;
+    std::vector<int> bsr_rows;    // host copy: first rows of the two quads of every row block (2 * nrb)
     int bsr_nbox[4] = {0, 0, 0, 0};  // ring size (boxes) that allows d chunks of lookahead, d = 0..3
     int bsr_maxf = 0;
     int64_t bsr_frags = 0;
