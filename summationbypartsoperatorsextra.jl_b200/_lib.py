@@ -12,7 +12,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsbp_b200.so")
+LIB_PATH = os.environ.get("SBP_B200_LIB") or os.path.join(_HERE, "libsbp_b200.so")  # override: experiment builds
 CSRC = os.path.join(_HERE, "csrc")
 
 SBP_OK, SBP_EINVAL, SBP_EDIM, SBP_ECUDA, SBP_ENOMEM, SBP_ENCCL, SBP_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6

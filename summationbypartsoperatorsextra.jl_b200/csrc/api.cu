@@ -321,7 +321,7 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
 //    (the stream continues across the tiles of a CTA, nbt boxes per tile).
 static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, const std::vector<int>& col,
                          const std::vector<double>& val) {
-    constexpr int CH = 4;  // == kBsrCH
+    constexpr int CH = kBsrCH;
     constexpr int BX = kBsrBX;
     const int nq = (N + 3) / 4;
     auto union_of = [&](int q, std::vector<int>& u) {
@@ -689,7 +689,7 @@ int32_t sbp_op_destroy(sbp_op* op) {
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
                     op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
-                    op->d_rbmask};
+                    op->d_rb_bdiag};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -812,13 +812,14 @@ int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h
     int32_t rc = upload(&op->d_b, b);
     if (!rc) rc = upload(&op->d_mode, mode);
     if (!rc && A->variant == SBP_KERNEL_BSR_DMMA) {
-        std::vector<int> rbmask(A->bsr_nrb, 0);  // bit r <=> row r of the block (quad A rows 0..3, quad B rows 4..7)
+        // b_j of every block row in block order (quad A rows 0..3, quad B rows 4..7); 0 where no SAT applies
+        std::vector<double> rbb(8 * (size_t)A->bsr_nrb, 0.0);
         for (int rb = 0; rb < A->bsr_nrb; rb++)
             for (int r = 0; r < 8; r++) {
                 const int i = (r < 4 ? A->bsr_rows[2 * rb] : A->bsr_rows[2 * rb + 1] - 4) + r;
-                if (i < N && h_mode[i] == 1) rbmask[rb] |= 1 << r;
+                if (i < N && h_mode[i] == 1) rbb[8 * (size_t)rb + r] = h_b[i];
             }
-        rc = upload(&op->d_rbmask, rbmask);
+        rc = upload(&op->d_rb_bdiag, rbb);
     }
     if (!rc) rc = upload(&op->d_q_consts, qc);
     if (!rc) {

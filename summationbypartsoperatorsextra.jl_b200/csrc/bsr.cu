@@ -34,8 +34,6 @@
 
 namespace sbp {
 
-constexpr int kBsrCH = 4;       // row blocks per chunk
-constexpr int kBsrGroups = 2;   // consumer groups, alternating chunks
 constexpr int kBsrMaxStages = 4;
 // consumer warps = kBsrGroups * kBsrCH * MH: warp = (group, row block of the chunk, m-half); a warp owns MTW m-tiles
 // (8 instances each) of the tile's TI = 8 * MTW * MH instances; + 1 producer warp
@@ -49,12 +47,12 @@ struct BsrParams {
     const int4* __restrict__ chmeta;  // [nch] {first fragment, end fragment, boxlo, boxhi}: boxes [0, boxhi) of the tile are
                                       // resident once the chunk has been staged; no later chunk touches a box below boxlo
     int N, nrb, nch, nbox, nbt, maxf, nst;  // nbox ring slots, nbt boxes per tile, nst pipeline stages
+    int pf;                           // L2 prefetch distance in boxes
     int rb_first, rb_last;            // row blocks holding row 0 and row N-1 (1D SATs)
     long long B;
     double alpha, beta;
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
-    const int* __restrict__ rbmask;   // [nrb] bit r set <=> row r of the block is an inflow node
-    const double* __restrict__ bdiag;
+    const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows
     const double* __restrict__ g;
     long long g_stride;
     Sat1D sat;                        // fused 1D SATs (rows 0 and N-1)
@@ -67,6 +65,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
             "r"(smem_u32(smem_dst)),
         "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
         : "memory");
+}
+
+// L2 prefetch of a box (no shared memory, no completion): hides the DRAM latency of the TMA load that follows later
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tmap), "r"(x), "r"(y)
+                 : "memory");
 }
 
 template <int MTW, int MH, int SAT, bool VEC>
@@ -86,6 +90,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
     const int N = p.N, nst = p.nst, nbox = p.nbox;
     const long long ntiles = (p.B + TI - 1) / TI;
     const int stepb = p.nbt % nbox;  // ring offset advance per tile (in boxes)
+    const bool alpha_m1 = p.alpha == -1.0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
@@ -98,31 +103,61 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
 
     if (warp == CONS) {
         // ------------------------------- producer: one elected thread issues TMA -------------------------------
+        // A single thread runs this loop; every instruction is on the critical path of the pipeline (a stage cannot be
+        // refilled faster than one trip through it), so it is kept to a few dozen instructions: ring slot and box
+        // coordinates advance incrementally, the chunk constants of the next item are fetched before the wait.
         if (lane == 0) {
-            int st = 0, round = 0, off = 0;
+            int st = 0, round = 0;
+            int slot = 0;   // ring slot of the next box to request
+            const uint32_t s_u32 = smem_u32(s_u), s_val32 = smem_u32(s_val), s_pos32 = smem_u32(s_pos);
+            const uint32_t full32 = smem_u32(&bar_full[0]);
+            const int pfx = p.pf * BX;
+            int4 cm = __ldg(p.chmeta);
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
-                int jb = 0;  // boxes of this tile already requested
+                const bool has_next = tile + gridDim.x < ntiles;
+                int jb = 0, x = 0;  // boxes of this tile already requested, node coordinate of the next box
                 for (int c = 0; c < p.nch; c++) {
+                    const int4 cmn = __ldg(p.chmeta + (c + 1 < p.nch ? c + 1 : 0));
                     if (round > 0) mbar_wait(&bar_empty[st], (round - 1) & 1);
-                    const int4 cm = __ldg(p.chmeta + c);
-                    const int jn = cm.w, f0 = cm.x, f1 = cm.y;
-                    const unsigned vbytes = (unsigned)(f1 - f0) * 256u, pbytes = (unsigned)(f1 - f0) * 16u;
-                    mbar_arrive_expect_tx(&bar_full[st], (unsigned)(jn - jb) * (unsigned)(BOX * 8) + vbytes + pbytes);
-                    for (int j = jb; j < jn; j++) {
-                        int slot = off + j % nbox;
-                        if (slot >= nbox) slot -= nbox;
-                        tma_load_2d(s_u + (size_t)slot * BOX, &tmap, j * BX, b0, &bar_full[st]);
+                    const int jn = cm.w;
+                    const unsigned nfr = (unsigned)(cm.y - cm.x);
+                    const uint32_t bar = full32 + 8u * st;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                                 "r"((unsigned)(jn - jb) * (unsigned)(BOX * 8) + nfr * 272u)
+                                 : "memory");
+                    for (; jb < jn; jb++, x += BX) {
+                        asm volatile(
+                            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+                            "%3}], [%4];\n" ::"r"(s_u32 + (uint32_t)slot * (uint32_t)(BOX * 8)),
+                            "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
+                            : "memory");
+                        if (++slot == nbox) slot = 0;
+                        // L2 prefetch cursor p.pf boxes ahead (this tile, or the head of the CTA's next tile)
+                        const int xp = x + pfx;
+                        if (xp < N)
+                            tma_prefetch_2d(&tmap, xp, b0);
+                        else if (has_next && xp - p.nbt * BX < N)
+                            tma_prefetch_2d(&tmap, xp - p.nbt * BX, b0 + (int)gridDim.x * TI);
                     }
-                    if (f1 > f0) {
-                        bulk_g2s(s_val + (size_t)st * p.maxf * 32, p.val + (size_t)f0 * 32, vbytes, &bar_full[st]);
-                        bulk_g2s(s_pos + (size_t)st * p.maxf * 4, p.pos + (size_t)f0 * 4, pbytes, &bar_full[st]);
+                    if (nfr) {
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                s_val32 + (uint32_t)st * (uint32_t)(p.maxf * 256)),
+                            "l"(p.val + (size_t)cm.x * 32), "r"(nfr * 256u), "r"(bar)
+                            : "memory");
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                                s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 16)),
+                            "l"(p.pos + (size_t)cm.x * 4), "r"(nfr * 16u), "r"(bar)
+                            : "memory");
                     }
-                    jb = jn;
                     if (++st == nst) st = 0, round++;
+                    cm = cmn;
                 }
-                off += stepb;
-                if (off >= nbox) off -= nbox;
+                // boxes of the tile that no chunk needs are skipped: keep slot == (virtual box index) mod nbox
+                slot += (p.nbt - jb) % nbox;
+                if (slot >= nbox) slot -= nbox;
             }
         }
         return;
@@ -134,29 +169,22 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
     const int i0 = mh * 8 * MTW;  // first instance (tile row) of this warp
     const double* su = s_u + (i0 + g) * BX;
 
-    // per-item operator constants (independent of the tile): fetched one item ahead so that their L2 latency is hidden
+    // per-item operator constants (independent of the tile), fetched one item ahead with independent loads
     struct Meta {
-        int frel, nf, r0, blo, mask;
-        double sb0, sb1;
-        bool active;
+        int4 rb;       // {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
+        int blo;       // lowest box of the chunk's window
+        double2 sb;    // SAT coefficients of the lane's two rows (0: no SAT)
     };
     auto load_meta = [&](int c) {
         Meta m;
         const int rb = c * kBsrCH + slotw;
-        m.active = rb < p.nrb;
-        m.frel = m.nf = m.blo = m.mask = 0;
-        m.r0 = N;
-        m.sb0 = m.sb1 = 0.0;
-        if (m.active) {
-            const int4 r = __ldg(p.rbmeta + rb);
-            m.frel = r.x, m.nf = r.y;
-            m.r0 = (t < 2 ? r.z : r.w - 4) + 2 * t;  // lane owns rows r0, r0 + 1 (pair t of the block)
+        m.rb = make_int4(0, 0, N, N + 4);
+        m.blo = 0;
+        m.sb = make_double2(0.0, 0.0);
+        if (rb < p.nrb) {
+            m.rb = __ldg(p.rbmeta + rb);
             m.blo = __ldg(p.chmeta + c).z;
-            if (SAT == 1) {
-                m.mask = (__ldg(p.rbmask + rb) >> (2 * t)) & 3;
-                if (m.mask & 1) m.sb0 = __ldg(p.bdiag + m.r0);
-                if (m.mask & 2) m.sb1 = __ldg(p.bdiag + m.r0 + 1);
-            }
+            if (SAT == 1) m.sb = __ldg(reinterpret_cast<const double2*>(p.rb_bdiag) + rb * 4 + t);
         }
         return m;
     };
@@ -192,7 +220,12 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
         const long long b0 = tile * TI;
         const int nb = (p.B - b0) < TI ? (int)(p.B - b0) : TI;
         const int rb = c * kBsrCH + slotw;
-        const int r0 = m.r0, blo = m.blo, mask = m.mask, nf = m.nf;
+        const bool active = rb < p.nrb;
+        const int4 rbm = m.rb;
+        const double2 sb = m.sb;
+        const int r0 = (t < 2 ? rbm.z : rbm.w - 4) + 2 * t;  // lane owns rows r0, r0 + 1 (pair t of the block)
+        const int blo = m.blo, nf = rbm.y;
+        const int mask = (SAT == 1) ? ((sb.x != 0.0 ? 1 : 0) | (sb.y != 0.0 ? 2 : 0)) : 0;
         int cb = blo % nbox + off;  // ring slot of box blo in this tile
         if (cb >= nbox) cb -= nbox;
         // element offset of (box-relative, column) code q inside the ring
@@ -204,29 +237,35 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
         double acc[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
-        double u0[MT], u1[MT];  // SAT == 1: own-row values; SAT == 2: the finished SAT terms of rows r0, r0 + 1
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) u0[mt] = u1[mt] = 0.0;
 
+        // boundary data shared by the batch (g_stride == 0): requested before the wait, consumed in the epilogue
+        double gs0 = 0.0, gs1 = 0.0;
+        if (SAT == 1 && mask && p.g_stride == 0) {
+            if (mask & 1) gs0 = __ldg(p.g + r0);
+            if (mask & 2) gs1 = __ldg(p.g + r0 + 1);
+        }
         mbar_wait(&bar_full[st], round & 1);
-        if (m.active) {
-            const double* sv = s_val + (size_t)st * p.maxf * 32 + (size_t)m.frel * 32 + lane;
-            const int* sp = s_pos + (size_t)st * p.maxf * 4 + m.frel * 4 + t;
-            if (nf > 0) {
-                // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
-                double b_cur = sv[0], a_cur[MT];
-                {
-                    const int o0 = ring_off(sp[0]);
+        {
+            const double* sv = s_val + (size_t)st * p.maxf * 32 + (size_t)rbm.x * 32 + lane;
+            const int* sp = s_pos + (size_t)st * p.maxf * 4 + rbm.x * 4 + t;
+            const int nfe = active ? nf : 0;
+            // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
+            double b_cur = 0.0, a_cur[MT];
+            int o_nxt = 0;
+            if (nfe > 0) {
+                b_cur = sv[0];
+                const int o0 = ring_off(sp[0]);
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * 8 * BX + o0];
-                }
-                int o_nxt = ring_off(sp[nf > 1 ? 4 : 0]);
-                for (int f = 1; f < nf; f++) {
+                for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * 8 * BX + o0];
+                o_nxt = ring_off(sp[nfe > 1 ? 4 : 0]);
+            }
+            if (nfe > 0) {
+                for (int f = 1; f < nfe; f++) {
                     const double b_nxt = sv[f * 32];
                     double a_nxt[MT];
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * 8 * BX + o_nxt];
-                    o_nxt = ring_off(sp[(f + 1 < nf ? f + 1 : f) * 4]);
+                    o_nxt = ring_off(sp[(f + 1 < nfe ? f + 1 : f) * 4]);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
                     b_cur = b_nxt;
@@ -236,14 +275,32 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
             }
-            if (SAT == 1 && mask) {  // own-row values (the chunk's own rows are inside its window)
+        }
+        if (active) {
+            // acc <- alpha * acc (the RHS calls with alpha = -1: a sign flip instead of FP64 multiplies), then the SAT
+            // terms are added in place while the stage is still held (they read the own-row values from the ring)
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                if (alpha_m1) {
+                    acc[mt][0] = -acc[mt][0], acc[mt][1] = -acc[mt][1];
+                } else {
+                    acc[mt][0] *= p.alpha, acc[mt][1] *= p.alpha;
+                }
+            }
+            if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
                 const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
                 const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
                 const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
-                    u0[mt] = su[mt * 8 * BX + o0];
-                    u1[mt] = su[mt * 8 * BX + o1];
+                    if (p.g_stride != 0) {  // per-instance boundary data
+                        const int il = i0 + mt * 8 + g;
+                        const double* gp = p.g + (b0 + (il < nb ? il : 0)) * p.g_stride + r0;
+                        if (mask & 1) gs0 = __ldg(gp);
+                        if (mask & 2) gs1 = __ldg(gp + 1);
+                    }
+                    if (mask & 1) acc[mt][0] += sb.x * (su[mt * 8 * BX + o0] - gs0);
+                    if (mask & 2) acc[mt][1] += sb.y * (su[mt * 8 * BX + o1] - gs1);
                 }
             }
             if (SAT == 2 && (rb == p.rb_first || rb == p.rb_last)) {
@@ -268,46 +325,32 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
                     const int il = mt * 8 + g;
                     const double vl = __shfl_sync(0xffffffffu, sl[il >> 5], il & 31);
                     const double vr = __shfl_sync(0xffffffffu, sr[il >> 5], il & 31);
-                    if (r0 == 0) u0[mt] = vl;
-                    if (r0 == N - 1) u0[mt] += vr;
-                    if (r0 + 1 == N - 1) u1[mt] = vr;
+                    if (r0 == 0) acc[mt][0] += vl;
+                    if (r0 == N - 1) acc[mt][0] += vr;
+                    if (r0 + 1 == N - 1) acc[mt][1] += vr;
                 }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);  // the stage (and the ring slots behind it) may be refilled
-        if (m.active) {
+        if (active && r0 < N) {
             // ---- epilogue: lane owns rows r0, r0+1 of instance i0 + 8mt + g ----
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 const int il = i0 + mt * 8 + g;
                 if (il >= nb) continue;
-                const long long inst = b0 + il;
-                double y0 = p.alpha * acc[mt][0], y1 = p.alpha * acc[mt][1];
-                if (SAT == 1 && mask) {
-                    const double* gp = p.g + inst * p.g_stride + r0;
-                    if (mask & 1) y0 += m.sb0 * (u0[mt] - __ldg(gp));
-                    if (mask & 2) y1 += m.sb1 * (u1[mt] - __ldg(gp + 1));
-                }
-                if (SAT == 2) {
-                    y0 += u0[mt];
-                    y1 += u1[mt];
-                }
-                double* yp = p.dU + inst * N + r0;
-                if (VEC) {  // N even: r0 + 1 < N whenever r0 < N
-                    if (r0 < N) {
-                        if (p.beta != 0.0) {
-                            const double2 o = *reinterpret_cast<const double2*>(yp);
-                            y0 = fma(p.beta, o.x, y0);
-                            y1 = fma(p.beta, o.y, y1);
-                        }
-                        stg_stream2(yp, y0, y1);
+                double y0 = acc[mt][0], y1 = acc[mt][1];
+                double* yp = p.dU + (b0 + il) * N + r0;
+                if (VEC) {  // N even: row r0 + 1 exists
+                    if (p.beta != 0.0) {
+                        const double2 o = *reinterpret_cast<const double2*>(yp);
+                        y0 = fma(p.beta, o.x, y0);
+                        y1 = fma(p.beta, o.y, y1);
                     }
+                    stg_stream2(yp, y0, y1);
                 } else {
-                    if (r0 < N) {
-                        if (p.beta != 0.0) y0 = fma(p.beta, yp[0], y0);
-                        stg_stream1(yp, y0);
-                    }
+                    if (p.beta != 0.0) y0 = fma(p.beta, yp[0], y0);
+                    stg_stream1(yp, y0);
                     if (r0 + 1 < N) {
                         if (p.beta != 0.0) y1 = fma(p.beta, yp[1], y1);
                         stg_stream1(yp + 1, y1);
@@ -320,6 +363,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
 }
 
 static size_t bsr_smem(const sbp_op* op, int MT, int D) {
+    const size_t nch = (op->bsr_nrb + kBsrCH - 1) / kBsrCH;
+    (void)nch;
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + (size_t)(D + 1) * op->bsr_maxf * (32 * 8 + 4 * 4);
 }
 static bool bsr_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D) {
@@ -408,12 +453,11 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.B = B;
     p.alpha = alpha * op->scale;
     p.beta = beta;
-    p.rbmask = adv ? adv->d_rbmask : nullptr;
-    p.bdiag = adv ? adv->d_b : nullptr;
+    p.rb_bdiag = adv ? adv->d_rb_bdiag : nullptr;
     p.g = g;
     p.g_stride = g_stride;
     if (sat) p.sat = *sat;
-    const int satmode = (adv && adv->d_rbmask) ? 1 : (sat && sat->enabled ? 2 : 0);
+    const int satmode = (adv && adv->d_rb_bdiag) ? 1 : (sat && sat->enabled ? 2 : 0);
     const bool vec = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;  // N is even
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller
@@ -428,7 +472,8 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     int MT = 8;
     while (MT > 1 && !bsr_fits(ctx, op, MT, 1)) MT >>= 1;
     while (MT > 1 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT >>= 1;
-    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 8) && bsr_fits(ctx, op, forced_mt, 0))
+    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 6 || forced_mt == 8) &&
+        bsr_fits(ctx, op, forced_mt, 0))
         MT = forced_mt;
     int D = 0;
     for (int d = 1; d < kBsrMaxStages; d++)
@@ -437,26 +482,31 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
                 bsr_smem(op, MT, D));
     p.nbox = op->bsr_nbox[D];
     p.nst = D + 1;
+    static int pf_env = -1;
+    if (pf_env < 0) {
+        const char* e = getenv("SBP_BSR_PREFETCH");
+        pf_env = e ? atoi(e) : 0;
+    }
+    p.pf = pf_env;
     const size_t smem = bsr_smem(op, MT, D);
-    // MT m-tiles per tile, split over two warps per row block (16 consumer warps) except for single m-tile tiles;
-    // SBP_BSR_MH=1 keeps one warp per row block (8 consumer warps, MT m-tiles each)
+    // one consumer warp per row block of the chunk, MT m-tiles each (SBP_BSR_MH=2: two warps per row block, MT/2 each)
     static int forced_mh = -1;
     if (forced_mh < 0) {
         const char* e = getenv("SBP_BSR_MH");
         forced_mh = e ? atoi(e) : 0;
     }
-    if (forced_mh == 1) {
+    if (forced_mh == 2 && MT >= 2) {
         switch (MT) {
-            case 8: return launch_bsr_mt<8, 1>(ctx, p, smem, satmode, vec);
-            case 4: return launch_bsr_mt<4, 1>(ctx, p, smem, satmode, vec);
-            case 2: return launch_bsr_mt<2, 1>(ctx, p, smem, satmode, vec);
-            default: return launch_bsr_mt<1, 1>(ctx, p, smem, satmode, vec);
+            case 8: return launch_bsr_mt<4, 2>(ctx, p, smem, satmode, vec);
+            case 4: return launch_bsr_mt<2, 2>(ctx, p, smem, satmode, vec);
+            default: return launch_bsr_mt<1, 2>(ctx, p, smem, satmode, vec);
         }
     }
     switch (MT) {
-        case 8: return launch_bsr_mt<4, 2>(ctx, p, smem, satmode, vec);
-        case 4: return launch_bsr_mt<2, 2>(ctx, p, smem, satmode, vec);
-        case 2: return launch_bsr_mt<1, 2>(ctx, p, smem, satmode, vec);
+        case 8: return launch_bsr_mt<8, 1>(ctx, p, smem, satmode, vec);
+        case 6: return launch_bsr_mt<6, 1>(ctx, p, smem, satmode, vec);
+        case 4: return launch_bsr_mt<4, 1>(ctx, p, smem, satmode, vec);
+        case 2: return launch_bsr_mt<2, 1>(ctx, p, smem, satmode, vec);
         default: return launch_bsr_mt<1, 1>(ctx, p, smem, satmode, vec);
     }
 }

@@ -28,7 +28,20 @@ void set_error(const char* fmt, ...);
         }                                \
     } while (0)
 
-constexpr int kBsrBX = 36;  // nodes per TMA box of the block-sparse kernel: 36 = 4 (mod 16) doubles => conflict-free gathers
+// block-sparse kernel (bsr.cu) geometry, shared by the host-side image builder (api.cu) and the kernel
+#ifndef SBP_BSR_BX
+#define SBP_BSR_BX 20
+#endif
+#ifndef SBP_BSR_CH
+#define SBP_BSR_CH 8
+#endif
+#ifndef SBP_BSR_G
+#define SBP_BSR_G 1
+#endif
+constexpr int kBsrBX = SBP_BSR_BX;     // nodes per TMA box: 4 (mod 16) doubles => conflict-free A-fragment gathers
+constexpr int kBsrCH = SBP_BSR_CH;     // row blocks per chunk
+constexpr int kBsrGroups = SBP_BSR_G;  // consumer groups, alternating chunks
+static_assert(kBsrBX % 16 == 4, "box rows must be 4 (mod 16) doubles");
 constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
 
 }  // namespace sbp
@@ -103,7 +116,7 @@ struct sbp_op {
     double* d_bnd_tau = nullptr;
     double* d_a = nullptr;
     double* d_q_consts = nullptr;  // per-node constants for the analysis quantities
-    int* d_rbmask = nullptr;       // 2D bundle over a block-sparse operator: inflow rows of every 8-row block (bit mask)
+    double* d_rb_bdiag = nullptr;  // 2D bundle over a block-sparse operator: b_j of every block row (block order), 0 = no SAT
     double sat_a0 = 1.0, sat_aN = 1.0, sat_w0 = 1.0, sat_wN = 1.0;  // 1D bundle: end speeds and end weights
 };
 
