@@ -47,7 +47,6 @@ struct BsrParams {
     const int4* __restrict__ chmeta;  // [nch] {first fragment, end fragment, boxlo, boxhi}: boxes [0, boxhi) of the tile are
                                       // resident once the chunk has been staged; no later chunk touches a box below boxlo
     int N, nrb, nch, nbox, nbt, maxf, nst;  // nbox ring slots, nbt boxes per tile, nst pipeline stages
-    int pf;                           // L2 prefetch distance in boxes
     int rb_first, rb_last;            // row blocks holding row 0 and row N-1 (1D SATs)
     long long B;
     double alpha, beta;
@@ -67,15 +66,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
-// L2 prefetch of a box (no shared memory, no completion): hides the DRAM latency of the TMA load that follows later
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(tmap), "r"(x), "r"(y)
+// TMA 2-D tensor store: box {4 rows, instances} from shared memory -> dU (bulk async-group completion); rows beyond N
+// and instances beyond B are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int x, int y, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(x),
+                 "r"(y), "r"(smem_u32(smem_src))
                  : "memory");
 }
 
-template <int MTW, int MH, int SAT, bool VEC>
-__global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
-    k_bsr(const BsrParams p, const __grid_constant__ CUtensorMap tmap) {
+// OUT: how results leave the SM.  0: 8-byte stores (dU not 16-byte aligned), 1: 16-byte stores, 2: staged in shared
+// memory and written by TMA tensor stores (beta == 0): asynchronous, so the output stream overlaps the next chunk's
+// tensor work instead of stalling every warp of the CTA on the store queue at the same time.
+template <int MTW, int MH, int SAT, int OUT>
+__global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
+    k_bsr(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
+    constexpr bool VEC = OUT != 0;
     constexpr int MT = MTW;
     constexpr int TI = 8 * MTW * MH;
     constexpr int CONS = kBsrGroups * kBsrCH * MH;  // consumer warps
@@ -86,6 +91,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
     int* s_pos = reinterpret_cast<int*>(s_val + (size_t)p.nst * p.maxf * 32);        // nst * maxf * 4
+    // output staging, per consumer warp: [quad A | quad B][8 * MTW instances][4 rows]  (128-byte aligned)
+    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)p.nst * p.maxf * 4 + 31) & ~(size_t)31));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N, nst = p.nst, nbox = p.nbox;
     const long long ntiles = (p.B + TI - 1) / TI;
@@ -94,63 +101,63 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
-            mbar_init(&bar_full[s], 1);              // the producer's arrive.expect_tx
+            mbar_init(&bar_full[s], 2);              // the two producers' arrive.expect_tx
             mbar_init(&bar_empty[s], CONS);          // lane 0 of every consumer warp
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == CONS) {
-        // ------------------------------- producer: one elected thread issues TMA -------------------------------
-        // A single thread runs this loop; every instruction is on the critical path of the pipeline (a stage cannot be
-        // refilled faster than one trip through it), so it is kept to a few dozen instructions: ring slot and box
-        // coordinates advance incrementally, the chunk constants of the next item are fetched before the wait.
+    if (warp >= CONS) {
+        // ------------------------------------------- producers -------------------------------------------
+        // Two single-thread producers (two warps, so that they run concurrently): warp CONS requests the boxes of the
+        // batch, warp CONS + 1 the operator fragments.  Each TMA-class instruction costs a thread ~200 cycles of issue
+        // time and every trip through this loop is on the critical path of the pipeline (a stage cannot be refilled
+        // faster than one trip), so the work is split and each loop is kept to a few dozen instructions: ring slot and
+        // box coordinates advance incrementally, the chunk constants of the next item are fetched before the wait.
         if (lane == 0) {
+            const bool boxes = warp == CONS;
             int st = 0, round = 0;
             int slot = 0;   // ring slot of the next box to request
             const uint32_t s_u32 = smem_u32(s_u), s_val32 = smem_u32(s_val), s_pos32 = smem_u32(s_pos);
             const uint32_t full32 = smem_u32(&bar_full[0]);
-            const int pfx = p.pf * BX;
             int4 cm = __ldg(p.chmeta);
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
-                const bool has_next = tile + gridDim.x < ntiles;
                 int jb = 0, x = 0;  // boxes of this tile already requested, node coordinate of the next box
                 for (int c = 0; c < p.nch; c++) {
                     const int4 cmn = __ldg(p.chmeta + (c + 1 < p.nch ? c + 1 : 0));
                     if (round > 0) mbar_wait(&bar_empty[st], (round - 1) & 1);
-                    const int jn = cm.w;
-                    const unsigned nfr = (unsigned)(cm.y - cm.x);
                     const uint32_t bar = full32 + 8u * st;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
-                                 "r"((unsigned)(jn - jb) * (unsigned)(BOX * 8) + nfr * 272u)
-                                 : "memory");
-                    for (; jb < jn; jb++, x += BX) {
-                        asm volatile(
-                            "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
-                            "%3}], [%4];\n" ::"r"(s_u32 + (uint32_t)slot * (uint32_t)(BOX * 8)),
-                            "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
-                            : "memory");
-                        if (++slot == nbox) slot = 0;
-                        // L2 prefetch cursor p.pf boxes ahead (this tile, or the head of the CTA's next tile)
-                        const int xp = x + pfx;
-                        if (xp < N)
-                            tma_prefetch_2d(&tmap, xp, b0);
-                        else if (has_next && xp - p.nbt * BX < N)
-                            tma_prefetch_2d(&tmap, xp - p.nbt * BX, b0 + (int)gridDim.x * TI);
-                    }
-                    if (nfr) {
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                                s_val32 + (uint32_t)st * (uint32_t)(p.maxf * 256)),
-                            "l"(p.val + (size_t)cm.x * 32), "r"(nfr * 256u), "r"(bar)
-                            : "memory");
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                                s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 16)),
-                            "l"(p.pos + (size_t)cm.x * 4), "r"(nfr * 16u), "r"(bar)
-                            : "memory");
+                    if (boxes) {
+                        const int jn = cm.w;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                                     "r"((unsigned)(jn - jb) * (unsigned)(BOX * 8))
+                                     : "memory");
+                        for (; jb < jn; jb++, x += BX) {
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
+                                "{%2, %3}], [%4];\n" ::"r"(s_u32 + (uint32_t)slot * (uint32_t)(BOX * 8)),
+                                "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
+                                : "memory");
+                            if (++slot == nbox) slot = 0;
+                        }
+                    } else {
+                        const unsigned nfr = (unsigned)(cm.y - cm.x);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(nfr * 272u)
+                                     : "memory");
+                        if (nfr) {
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                                    "r"(s_val32 + (uint32_t)st * (uint32_t)(p.maxf * 256)),
+                                "l"(p.val + (size_t)cm.x * 32), "r"(nfr * 256u), "r"(bar)
+                                : "memory");
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                                    "r"(s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 16)),
+                                "l"(p.pos + (size_t)cm.x * 4), "r"(nfr * 16u), "r"(bar)
+                                : "memory");
+                        }
                     }
                     if (++st == nst) st = 0, round++;
                     cm = cmn;
@@ -333,7 +340,27 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);  // the stage (and the ring slots behind it) may be refilled
-        if (active && r0 < N) {
+        if (OUT == 2) {
+            // ---- epilogue through TMA: lane (g,t) deposits rows r0, r0+1 of instance 8mt + g in the warp's staging
+            //      buffer; one elected lane stores quad A and quad B as {4 rows x 8*MTW instances} boxes ----
+            double* so = s_out + (size_t)warp * (2 * 8 * MTW * 4);
+            if (lane == 0) bulk_wait_read<0>();  // the previous boxes of this warp have been read out of the buffer
+            __syncwarp();
+            if (active) {
+                double* sq = so + (t >> 1) * (8 * MTW * 4) + g * 4 + (t & 1) * 2;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+                    *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
+                fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    const int y = (int)b0 + i0;
+                    if (rbm.z < N) tma_store_2d(&tmap_out, rbm.z, y, so);
+                    if (rbm.w < N) tma_store_2d(&tmap_out, rbm.w, y, so + 8 * MTW * 4);
+                    bulk_commit();
+                }
+            }
+        } else if (active && r0 < N) {
             // ---- epilogue: lane owns rows r0, r0+1 of instance i0 + 8mt + g ----
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
@@ -360,12 +387,15 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 1) * 32)
         }
         m = mn;
     }
+    if (OUT == 2 && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
 }
 
 static size_t bsr_smem(const sbp_op* op, int MT, int D) {
     const size_t nch = (op->bsr_nrb + kBsrCH - 1) / kBsrCH;
     (void)nch;
-    return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + (size_t)(D + 1) * op->bsr_maxf * (32 * 8 + 4 * 4);
+    const size_t ops = ((size_t)(D + 1) * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
+    const size_t staging = (size_t)kBsrGroups * kBsrCH * 2 * 8 * MT * 4 * 8;  // per consumer warp: 2 quads x instances x 4 rows
+    return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
 static bool bsr_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D) {
     return bsr_smem(op, MT, D) + 1024 <= (size_t)ctx->smem_optin;
@@ -395,42 +425,56 @@ static PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
-template <int MTW, int MH, int SAT, bool VEC>
-static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr<MTW, MH, SAT, VEC>;
-    constexpr int TI = 8 * MTW * MH;
-    constexpr int THREADS = (kBsrGroups * kBsrCH * MH + 1) * 32;
-    // the batch as a 2-D tensor [B][N] of doubles; one box = kBsrBX nodes x TI instances
+static int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int box_nodes, int box_inst) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     SBP_REQUIRE(enc != nullptr, SBP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tmap;
-    const cuuint64_t dims[2] = {(cuuint64_t)p.N, (cuuint64_t)p.B};
-    const cuuint64_t strides[1] = {(cuuint64_t)p.N * 8};
-    const cuuint32_t box[2] = {(cuuint32_t)kBsrBX, (cuuint32_t)TI};
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)box_nodes, (cuuint32_t)box_inst};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(p.U), dims, strides, box, estr,
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SBP_REQUIRE(r == CUDA_SUCCESS, SBP_ECUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d B=%lld", (int)r, p.N, p.B);
+    SBP_REQUIRE(r == CUDA_SUCCESS, SBP_ECUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d B=%lld", (int)r, N, B);
+    return SBP_OK;
+}
+
+template <int MTW, int MH, int SAT, int OUT>
+static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
+    auto kern = k_bsr<MTW, MH, SAT, OUT>;
+    constexpr int TI = 8 * MTW * MH;
+    constexpr int THREADS = (kBsrGroups * kBsrCH * MH + 2) * 32;
+    // the batch as a 2-D tensor [B][N] of doubles; input boxes = kBsrBX nodes x TI instances, output boxes = one quad
+    // of rows x the 8*MTW instances of a consumer warp
+    CUtensorMap tmap, tmap_out;
+    int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
+    if (rc) return rc;
+    rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, 8 * MTW) : make_tmap(&tmap_out, p.U, p.N, p.B, kBsrBX, TI);
+    if (rc) return rc;
     SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const long long ntiles = (p.B + TI - 1) / TI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
-    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap);
+    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
 }
 
 template <int MTW, int MH>
-static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, bool vec) {
-    if (sat == 1)
-        return vec ? launch_bsr_k<MTW, MH, 1, true>(ctx, p, smem) : launch_bsr_k<MTW, MH, 1, false>(ctx, p, smem);
-    if (sat == 2)
-        return vec ? launch_bsr_k<MTW, MH, 2, true>(ctx, p, smem) : launch_bsr_k<MTW, MH, 2, false>(ctx, p, smem);
-    return vec ? launch_bsr_k<MTW, MH, 0, true>(ctx, p, smem) : launch_bsr_k<MTW, MH, 0, false>(ctx, p, smem);
+static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out) {
+#define SBP_BSR_OUT(S)                                                       \
+    switch (out) {                                                           \
+        case 2: return launch_bsr_k<MTW, MH, S, 2>(ctx, p, smem);            \
+        case 1: return launch_bsr_k<MTW, MH, S, 1>(ctx, p, smem);            \
+        default: return launch_bsr_k<MTW, MH, S, 0>(ctx, p, smem);           \
+    }
+    if (sat == 1) { SBP_BSR_OUT(1) }
+    if (sat == 2) { SBP_BSR_OUT(2) }
+    SBP_BSR_OUT(0)
+#undef SBP_BSR_OUT
 }
 
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
@@ -458,7 +502,14 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.g_stride = g_stride;
     if (sat) p.sat = *sat;
     const int satmode = (adv && adv->d_rb_bdiag) ? 1 : (sat && sat->enabled ? 2 : 0);
-    const bool vec = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;  // N is even
+    // output path: TMA tensor stores when dU is 16-byte aligned and beta == 0 (SBP_BSR_OUT=1 forces plain stores)
+    static int forced_out = -1;
+    if (forced_out < 0) {
+        const char* e = getenv("SBP_BSR_OUT");
+        forced_out = e ? atoi(e) : 2;
+    }
+    const bool aligned = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;  // N is even
+    const int vec = !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller
     // tiles so that every SM gets work.  SBP_BSR_MT / SBP_BSR_DEPTH override (tuning).
@@ -470,9 +521,10 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         forced_d = e ? atoi(e) : 99;
     }
     int MT = 8;
-    while (MT > 1 && !bsr_fits(ctx, op, MT, 1)) MT >>= 1;
-    while (MT > 1 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT >>= 1;
-    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 6 || forced_mt == 8) &&
+    auto smaller = [](int mt) { return mt == 8 ? 7 : mt == 7 ? 6 : mt == 6 ? 4 : mt >> 1; };
+    while (MT > 1 && !bsr_fits(ctx, op, MT, 1)) MT = smaller(MT);
+    while (MT > 1 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT = smaller(MT);
+    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 6 || forced_mt == 7 || forced_mt == 8) &&
         bsr_fits(ctx, op, forced_mt, 0))
         MT = forced_mt;
     int D = 0;
@@ -482,12 +534,6 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
                 bsr_smem(op, MT, D));
     p.nbox = op->bsr_nbox[D];
     p.nst = D + 1;
-    static int pf_env = -1;
-    if (pf_env < 0) {
-        const char* e = getenv("SBP_BSR_PREFETCH");
-        pf_env = e ? atoi(e) : 0;
-    }
-    p.pf = pf_env;
     const size_t smem = bsr_smem(op, MT, D);
     // one consumer warp per row block of the chunk, MT m-tiles each (SBP_BSR_MH=2: two warps per row block, MT/2 each)
     static int forced_mh = -1;
@@ -504,6 +550,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     }
     switch (MT) {
         case 8: return launch_bsr_mt<8, 1>(ctx, p, smem, satmode, vec);
+        case 7: return launch_bsr_mt<7, 1>(ctx, p, smem, satmode, vec);
         case 6: return launch_bsr_mt<6, 1>(ctx, p, smem, satmode, vec);
         case 4: return launch_bsr_mt<4, 1>(ctx, p, smem, satmode, vec);
         case 2: return launch_bsr_mt<2, 1>(ctx, p, smem, satmode, vec);
