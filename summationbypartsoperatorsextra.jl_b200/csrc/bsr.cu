@@ -7,26 +7,36 @@
 //
 // Why tensor cores for a sparse operator: the scalar kernel (sparse.cu) is bound by shared-memory wavefronts (8 B
 // gathered per FMA, bank conflicts from the irregular pattern, operator entries through L1).  Here the operator is cut
-// into ROW BLOCKS of 8 rows; the union of a block's columns is split into FRAGMENTS of 4 columns (any 4 columns: the
-// A operand is gathered).  One DMMA.8x8x4 multiplies a fragment (8 rows x 4 columns, zero padded) with 8 instances:
-//     A operand  lane (g,t) = U[instance 8mt+g][column c_t]      one conflict-free LDS.64 from the staged tile
-//     B operand  lane (g,t) = D[row 8rb+g][column c_t]            one LDS.64, reused by the MT m-tiles of the warp
-//     C          lane (g,t) = rows 8rb+2t, 8rb+2t+1 of instance 8mt+g  -> one 128-bit store
-// so a gathered 8-byte value feeds 16 flops instead of 2, and the access pattern of the gather is the same for every
-// operator (no bank conflicts for runs of consecutive columns).
+// into ROW BLOCKS of 8 rows (two aligned quads of 4 rows, paired on the host so that the union of their columns is
+// small: a 2 x 4 patch of a 2-D cloud); the union of a block's columns is split into FRAGMENTS of 4 columns (any 4
+// columns: the A operand is gathered).  One DMMA.8x8x4 multiplies a fragment (8 rows x 4 columns, zero padded) with 8
+// instances:
+//     A operand  lane (g,t) = U[instance 8mt+g][column c_t]      one LDS.64 from the staged boxes (conflict free when
+//                                                                 the 4 columns differ mod 4 -- arranged by the host)
+//     B operand  lane (g,t) = D[block row g][column c_t]          one LDS.64, reused by the MT m-tiles of the warp
+//     C          lane (g,t) = block rows 2t, 2t+1 of instance 8mt+g = one aligned pair of output rows
+// so a gathered 8-byte value feeds 16 flops instead of 2 and the gather pattern is the same for every operator.
 //
-// Streaming ring + warp specialisation: a tile of TI = 8*MT instances is NOT staged whole (N = 1296 x 64 instances =
-// 663 KB).  The batch is a 2-D tensor [instance][node]; it is streamed through shared memory in BOXES of kBsrBX = 36
-// consecutive nodes x TI instances, each fetched by ONE TMA tensor copy (cp.async.bulk.tensor.2d; out-of-range rows
-// and nodes are zero filled by the hardware).  36 doubles per row = 4 (mod 16): the 8 x 4 A-fragment gather is
-// bank-conflict free without swizzling.  Boxes live in a ring of NBOX slots (slot = virtual box index mod NBOX, the
-// virtual index keeps counting across the tiles of a CTA), so every node is read from HBM exactly once.  Row blocks
-// are processed in CHUNKS of 4; chunk c needs the nodes [lo_c, hi_c).  One elected PRODUCER thread issues, per chunk,
-// the boxes that complete [0, hi_c) plus two bulk copies with the chunk's operator fragments, all signalling the
-// "full" mbarrier of a pipeline stage; eight CONSUMER warps (two groups of four, alternating chunks) wait on it, run
-// the DMMA chain of one row block each and release the stage through its "empty" mbarrier.  No CTA-wide barrier in
-// the steady state: the epilogue of one warp overlaps the DMMAs of the others, and up to three chunks are in flight
-// while one is being multiplied.
+// Data movement (all asynchronous, all through the TMA):
+//  * The batch is a 2-D tensor [instance][node].  A tile of TI = 8*MT instances is NOT staged whole (N = 1296 x 56
+//    instances = 580 KB): it streams through shared memory in BOXES of kBsrBX = 20 consecutive nodes x TI instances,
+//    each fetched by ONE tensor copy (cp.async.bulk.tensor.2d; out-of-range instances and nodes are zero filled by
+//    the hardware).  20 doubles per row = 4 (mod 16): the 8 x 4 A-fragment gather is bank-conflict free without
+//    swizzling.  Boxes live in a ring (slot = virtual box index mod nbox; the virtual index keeps counting across the
+//    tiles of a CTA), so every node is read from HBM exactly once.
+//  * Row blocks are processed in CHUNKS of kBsrCH = 8; chunk c needs the boxes [boxlo_c, boxhi_c).  Two single-thread
+//    PRODUCERS (separate warps) wait on the "empty" mbarrier of a pipeline stage and request the boxes that complete
+//    [0, boxhi_c) resp. the chunk's operator fragments (two bulk copies from L2), all signalling the stage's "full"
+//    mbarrier.  Eight CONSUMER warps wait on it, run the DMMA chain of one row block each (MT accumulator tiles per
+//    warp, operands software-pipelined one fragment ahead), add the SAT terms from the ring and release the stage.
+//  * Results leave through TMA as well: each consumer warp deposits its C fragments in a private staging buffer and
+//    one elected lane stores the block's two quads as {4 rows x TI instances} tensor boxes (cp.async.bulk.tensor
+//    store, bulk async-group); the warp moves on to the next chunk at once.  With plain 16-byte stores every warp
+//    of the CTA stalled on the store queue at the end of every chunk (2100 of 5150 cycles per chunk, measured with
+//    clock64 stamps) while the tensor pipe idled; beta != 0 or an unaligned dU fall back to that path.
+//  * No CTA-wide barrier after the prologue.
+// Measured (profiles/r1f_*): BASELINE config 3 (N = 1296 cloud, 13.3 nnz/row, B = 65536, fused 2D SAT) 0.344 ms = 247
+// GDOF/s (scalar kernel: 0.80 ms); banded N = 104 apply 0.148 ms = 368 GDOF/s = 90% of the measured HBM peak.
 #include <algorithm>
 #include <cuda.h>
 #include "common.cuh"
@@ -36,7 +46,7 @@ namespace sbp {
 
 constexpr int kBsrMaxStages = 4;
 // consumer warps = kBsrGroups * kBsrCH * MH: warp = (group, row block of the chunk, m-half); a warp owns MTW m-tiles
-// (8 instances each) of the tile's TI = 8 * MTW * MH instances; + 1 producer warp
+// (8 instances each) of the tile's TI = 8 * MTW * MH instances; + 2 producer warps
 
 struct BsrParams {
     const double* __restrict__ U;
@@ -521,10 +531,10 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         forced_d = e ? atoi(e) : 99;
     }
     int MT = 8;
-    auto smaller = [](int mt) { return mt == 8 ? 7 : mt == 7 ? 6 : mt == 6 ? 4 : mt >> 1; };
+    auto smaller = [](int mt) { return mt > 4 ? mt - 1 : mt >> 1; };
     while (MT > 1 && !bsr_fits(ctx, op, MT, 1)) MT = smaller(MT);
     while (MT > 1 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT = smaller(MT);
-    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 6 || forced_mt == 7 || forced_mt == 8) &&
+    if ((forced_mt == 1 || forced_mt == 2 || forced_mt == 4 || forced_mt == 3 || forced_mt == 5 || forced_mt == 6 || forced_mt == 7 || forced_mt == 8) &&
         bsr_fits(ctx, op, forced_mt, 0))
         MT = forced_mt;
     int D = 0;
@@ -552,6 +562,8 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         case 8: return launch_bsr_mt<8, 1>(ctx, p, smem, satmode, vec);
         case 7: return launch_bsr_mt<7, 1>(ctx, p, smem, satmode, vec);
         case 6: return launch_bsr_mt<6, 1>(ctx, p, smem, satmode, vec);
+        case 5: return launch_bsr_mt<5, 1>(ctx, p, smem, satmode, vec);
+        case 3: return launch_bsr_mt<3, 1>(ctx, p, smem, satmode, vec);
         case 4: return launch_bsr_mt<4, 1>(ctx, p, smem, satmode, vec);
         case 2: return launch_bsr_mt<2, 1>(ctx, p, smem, satmode, vec);
         default: return launch_bsr_mt<1, 1>(ctx, p, smem, satmode, vec);
