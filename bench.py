@@ -262,11 +262,26 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
         u, du = S.DeviceBatch.from_torch(ctx, U), S.DeviceBatch.from_torch(ctx, Y)
         nnz = int(np.count_nonzero(semi.cache["A"]))
         r = bench(lambda i: semi(du, u, None, 0.1), B * N, 16.0, flops=2.0 * nnz * B)
-        r["N"], r["nnz_per_row"] = N, nnz / N
+        r["N"], r["nnz_per_row"], r["kernel"] = N, nnz / N, semi.device_op(ctx).info()["kernel"]
         out["config3_advection2d_rhs_sat"] = r
         del U, Y
     except Exception as e:  # pragma: no cover
         out["config3_advection2d_rhs_sat"] = {"error": str(e)[:200]}
+    try:  # config 1 batched: banded 1D FD-SBP operator N = 101 (examples/RBF_FSBP_advection.jl sizes), RHS with SATs
+        N, B = 101, 1 << 19
+        D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        D1.storage = "dense"  # odd N: smem-resident DMMA kernel with band skipping (the TMA kernel needs even N)
+        semi1 = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False,
+                                                                       lambda t: 0.3, lambda t: 0.0)
+        U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1
+        Y = torch.empty_like(U)
+        u, du = S.DeviceBatch.from_torch(ctx, U), S.DeviceBatch.from_torch(ctx, Y)
+        r = bench(lambda i: semi1(du, u, None, 0.1), B * N, 16.0)
+        r["N"], r["kernel"] = N, semi1.device_op(ctx).info()["kernel"]
+        out["config1_batched_banded_N101_rhs1d"] = r
+        del U, Y
+    except Exception as e:  # pragma: no cover
+        out["config1_batched_banded_N101_rhs1d"] = {"error": str(e)[:200]}
     try:  # config 5 (reduced batch): dense N = 4096 operator, B = 8192 -> DMMA DGEMM
         N, B = 4096, 8192
         rng = np.random.default_rng(0)

@@ -380,6 +380,9 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     }
     const int nrb = (int)rows.size() / 2, nch = (nrb + CH - 1) / CH;
     auto block_row = [&](int rb, int g) { return (g < 4 ? rows[2 * rb] : rows[2 * rb + 1] - 4) + g; };
+    // odd N: the batch is read through a pair-row view whose odd instances are shifted by one node (see bsr.cu), so a
+    // fragment carries two sets of ring codes: columns c (even instances) and c + 1 (odd instances)
+    const int PS = (N & 1) ? 8 : 4;
     std::vector<int> rbf(nrb + 1, 0), pos;
     std::vector<double> frag;
     std::vector<int> cmin(nch, N), cmax(nch, 0);
@@ -404,7 +407,7 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
         const int nf = ((int)u.size() + 3) / 4;
         const size_t f0 = frag.size() / 32;
         frag.resize((f0 + nf) * 32, 0.0);
-        pos.resize((f0 + nf) * 4, 0);
+        pos.resize((f0 + nf) * PS, 0);
         std::vector<int> where(u.size(), 0);  // union index -> 4 * fragment + t
         {
             std::vector<int> bucket[4];
@@ -423,7 +426,8 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
                     }
                 for (int t = 0; t < 4; t++) {
                     const int k = cols[t < taken ? t : 0];
-                    pos[(f0 + f) * 4 + t] = u[k];
+                    pos[(f0 + f) * PS + t] = u[k];
+                    if (PS == 8) pos[(f0 + f) * PS + 4 + t] = u[k] + 1;
                     if (t < taken) where[k] = 4 * f + t;
                 }
             }
@@ -447,14 +451,14 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     std::vector<int> blo(nch), bhi(nch);
     for (int c = 0, m = 0; c < nch; c++) {
         m = std::max(m, cmax[c]);
-        bhi[c] = (m + BX - 1) / BX;
+        bhi[c] = (m + (PS == 8 ? 1 : 0) + BX - 1) / BX;
     }
     for (int c = nch - 1, m = N; c >= 0; c--) {
         m = std::min(m, cmin[c]);
         blo[c] = m / BX;
     }
     for (int rb = 0; rb < nrb; rb++)
-        for (int f = rbf[rb] * 4; f < rbf[rb + 1] * 4; f++) {
+        for (int f = rbf[rb] * PS; f < rbf[rb + 1] * PS; f++) {
             const int n = pos[f];
             pos[f] = ((n / BX - blo[rb / CH]) << 8) | (n % BX);
         }
@@ -491,7 +495,7 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     op->bsr_frags = (int64_t)frag.size() / 32;
     if (frag.empty()) {
         frag.assign(32, 0.0);
-        pos.assign(4, 0);
+        pos.assign(PS, 0);
     }
     int32_t rc = upload(&op->d_bsr_val, frag);
     if (!rc) rc = upload(&op->d_bsr_pos, pos);

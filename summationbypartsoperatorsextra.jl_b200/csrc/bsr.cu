@@ -90,7 +90,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int x, int
 template <int MTW, int MH, int SAT, int OUT>
 __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     k_bsr(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
-    constexpr bool VEC = OUT != 0;
+    constexpr bool VEC = OUT == 1 || OUT == 2;
+    // PAIR (OUT == 3, odd N): the rows of the batch are not 16-byte multiples, so the batch is viewed as [B/2][2N]
+    // (two instances per tensor row); a box is fetched as two sub-boxes {nodes, TI/2 rows} at x and x + N, and lane g of
+    // an m-tile owns instance 8mt + 2(g&3) + (g>>2): a half-warp gathers 4 rows of ONE sub-box (conflict free)
+    constexpr bool PAIR = OUT == 3;
+    constexpr int MTS = PAIR ? 4 * kBsrBX : 8 * kBsrBX;  // smem distance between the m-tiles of a lane
+    // TMA box origins must be 16-byte aligned: the odd instances (which start at the odd element N of a pair row) are
+    // fetched from x + N - 1, i.e. shifted by one node; their ring codes are those of column + 1 (second half of the
+    // fragment's code array, PS = 8 codes per fragment)
+    constexpr int PS = PAIR ? 8 : 4;
     constexpr int MT = MTW;
     constexpr int TI = 8 * MTW * MH;
     constexpr int CONS = kBsrGroups * kBsrCH * MH;  // consumer warps
@@ -100,9 +109,9 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     __shared__ uint64_t bar_full[kBsrMaxStages], bar_empty[kBsrMaxStages];
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
-    int* s_pos = reinterpret_cast<int*>(s_val + (size_t)p.nst * p.maxf * 32);        // nst * maxf * 4
+    int* s_pos = reinterpret_cast<int*>(s_val + (size_t)p.nst * p.maxf * 32);        // nst * maxf * PS
     // output staging, per consumer warp: [quad A | quad B][8 * MTW instances][4 rows]  (128-byte aligned)
-    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)p.nst * p.maxf * 4 + 31) & ~(size_t)31));
+    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)p.nst * p.maxf * PS + 31) & ~(size_t)31));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = p.N, nst = p.nst, nbox = p.nbox;
     const long long ntiles = (p.B + TI - 1) / TI;
@@ -145,16 +154,24 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                                      "r"((unsigned)(jn - jb) * (unsigned)(BOX * 8))
                                      : "memory");
                         for (; jb < jn; jb++, x += BX) {
+                            const uint32_t dst = s_u32 + (uint32_t)slot * (uint32_t)(BOX * 8);
                             asm volatile(
                                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
-                                "{%2, %3}], [%4];\n" ::"r"(s_u32 + (uint32_t)slot * (uint32_t)(BOX * 8)),
-                                "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
+                                "{%2, %3}], [%4];\n" ::"r"(dst),
+                                "l"(&tmap), "r"(x), "r"(PAIR ? b0 / 2 : b0), "r"(bar)
                                 : "memory");
+                            if (PAIR)  // the odd instances of the pair rows
+                                asm volatile(
+                                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], "
+                                    "[%1, {%2, %3}], [%4];\n" ::"r"(dst + (uint32_t)(BOX * 4)),
+                                    "l"(&tmap), "r"(x + N - 1), "r"(b0 / 2), "r"(bar)
+                                    : "memory");
                             if (++slot == nbox) slot = 0;
                         }
                     } else {
                         const unsigned nfr = (unsigned)(cm.y - cm.x);
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(nfr * 272u)
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                                     "r"(nfr * (256u + 4u * PS))
                                      : "memory");
                         if (nfr) {
                             asm volatile(
@@ -164,8 +181,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                                 : "memory");
                             asm volatile(
                                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
-                                    "r"(s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 16)),
-                                "l"(p.pos + (size_t)cm.x * 4), "r"(nfr * 16u), "r"(bar)
+                                    "r"(s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 4 * PS)),
+                                "l"(p.pos + (size_t)cm.x * PS), "r"(nfr * 4u * PS), "r"(bar)
                                 : "memory");
                         }
                     }
@@ -184,7 +201,10 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     const int g = lane >> 2, t = lane & 3;
     const int grp = warp / (kBsrCH * MH), slotw = (warp / MH) % kBsrCH, mh = warp % MH;
     const int i0 = mh * 8 * MTW;  // first instance (tile row) of this warp
-    const double* su = s_u + (i0 + g) * BX;
+    // local instance of lane g in m-tile mt, and where an instance's row lives inside a box
+    auto inst_of = [&](int mt) { return PAIR ? 8 * mt + 2 * (g & 3) + (g >> 2) : 8 * mt + g; };
+    auto inst_off = [&](int il) { return PAIR ? (il & 1) * (TI / 2) * BX + (il >> 1) * BX : il * BX; };
+    const double* su = s_u + inst_off(i0 + inst_of(0));
 
     // per-item operator constants (independent of the tile), fetched one item ahead with independent loads
     struct Meta {
@@ -264,7 +284,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
         mbar_wait(&bar_full[st], round & 1);
         {
             const double* sv = s_val + (size_t)st * p.maxf * 32 + (size_t)rbm.x * 32 + lane;
-            const int* sp = s_pos + (size_t)st * p.maxf * 4 + rbm.x * 4 + t;
+            const int* sp = s_pos + (size_t)st * p.maxf * PS + rbm.x * PS + (PAIR ? 4 * (g >> 2) : 0) + t;
             const int nfe = active ? nf : 0;
             // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
             double b_cur = 0.0, a_cur[MT];
@@ -273,16 +293,16 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                 b_cur = sv[0];
                 const int o0 = ring_off(sp[0]);
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * 8 * BX + o0];
-                o_nxt = ring_off(sp[nfe > 1 ? 4 : 0]);
+                for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * MTS + o0];
+                o_nxt = ring_off(sp[nfe > 1 ? PS : 0]);
             }
             if (nfe > 0) {
                 for (int f = 1; f < nfe; f++) {
                     const double b_nxt = sv[f * 32];
                     double a_nxt[MT];
 #pragma unroll
-                    for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * 8 * BX + o_nxt];
-                    o_nxt = ring_off(sp[(f + 1 < nfe ? f + 1 : f) * 4]);
+                    for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * MTS + o_nxt];
+                    o_nxt = ring_off(sp[(f + 1 < nfe ? f + 1 : f) * PS]);
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
                     b_cur = b_nxt;
@@ -305,26 +325,30 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                 }
             }
             if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
-                const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
-                const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
-                const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
+                const int n0 = r0 + (PAIR ? (g >> 2) : 0);  // odd instances of a pair row are stored one node later
+                const int q0 = n0 / BX, q1 = (n0 + 1) / BX;
+                const int o0 = ring_off(((q0 - blo) << 8) | (n0 - q0 * BX));
+                const int o1 = ring_off(((q1 - blo) << 8) | (n0 + 1 - q1 * BX));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     if (p.g_stride != 0) {  // per-instance boundary data
-                        const int il = i0 + mt * 8 + g;
+                        const int il = i0 + inst_of(mt);
                         const double* gp = p.g + (b0 + (il < nb ? il : 0)) * p.g_stride + r0;
                         if (mask & 1) gs0 = __ldg(gp);
                         if (mask & 2) gs1 = __ldg(gp + 1);
                     }
-                    if (mask & 1) acc[mt][0] += sb.x * (su[mt * 8 * BX + o0] - gs0);
-                    if (mask & 2) acc[mt][1] += sb.y * (su[mt * 8 * BX + o1] - gs1);
+                    if (mask & 1) acc[mt][0] += sb.x * (su[mt * MTS + o0] - gs0);
+                    if (mask & 2) acc[mt][1] += sb.y * (su[mt * MTS + o1] - gs1);
                 }
             }
             if (SAT == 2 && (rb == p.rb_first || rb == p.rb_last)) {
                 // 1D SATs at rows 0 and N-1: one division per instance.  Lane l evaluates them for the warp's
                 // instances l (and l + 32) in parallel; the owners of the two rows fetch them by shuffle.
-                const int qR = (N - 1) / BX;
-                const int oL = ring_off((0 - blo) << 8), oR = ring_off(((qR - blo) << 8) | (N - 1 - qR * BX));
+                // code of a node inside the ring, for an instance of the given parity (odd: stored one node later)
+                auto node_off = [&](int n, int par) {
+                    const int nn = n + (PAIR ? par : 0), q = nn / BX;
+                    return ring_off(((q - blo) << 8) | (nn - q * BX));
+                };
                 double sl[(8 * MTW + 31) / 32], sr[(8 * MTW + 31) / 32];
 #pragma unroll
                 for (int k = 0; k < (8 * MTW + 31) / 32; k++) {
@@ -332,14 +356,14 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                     sl[k] = sr[k] = 0.0;
                     if (il < 8 * MTW && i0 + il < nb) {
                         const long long inst = b0 + i0 + il;
-                        const double* up = s_u + (size_t)(i0 + il) * BX;
-                        if (rb == p.rb_first) sl[k] = sat1d_left(p.sat, inst, p.sat.a0 * up[oL]);
-                        if (rb == p.rb_last) sr[k] = sat1d_right(p.sat, inst, p.sat.aN * up[oR]);
+                        const double* up = s_u + inst_off(i0 + il);
+                        if (rb == p.rb_first) sl[k] = sat1d_left(p.sat, inst, p.sat.a0 * up[node_off(0, il & 1)]);
+                        if (rb == p.rb_last) sr[k] = sat1d_right(p.sat, inst, p.sat.aN * up[node_off(N - 1, il & 1)]);
                     }
                 }
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
-                    const int il = mt * 8 + g;
+                    const int il = inst_of(mt);
                     const double vl = __shfl_sync(0xffffffffu, sl[il >> 5], il & 31);
                     const double vr = __shfl_sync(0xffffffffu, sr[il >> 5], il & 31);
                     if (r0 == 0) acc[mt][0] += vl;
@@ -374,7 +398,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
             // ---- epilogue: lane owns rows r0, r0+1 of instance i0 + 8mt + g ----
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                const int il = i0 + mt * 8 + g;
+                const int il = i0 + inst_of(mt);
                 if (il >= nb) continue;
                 double y0 = acc[mt][0], y1 = acc[mt][1];
                 double* yp = p.dU + (b0 + il) * N + r0;
@@ -403,7 +427,7 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
 static size_t bsr_smem(const sbp_op* op, int MT, int D) {
     const size_t nch = (op->bsr_nrb + kBsrCH - 1) / kBsrCH;
     (void)nch;
-    const size_t ops = ((size_t)(D + 1) * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
+    const size_t ops = ((size_t)(D + 1) * op->bsr_maxf * (32 * 8 + ((op->N & 1) ? 8 : 4) * 4) + 127) & ~(size_t)127;
     const size_t staging = (size_t)kBsrGroups * kBsrCH * 2 * 8 * MT * 4 * 8;  // per consumer warp: 2 quads x instances x 4 rows
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
@@ -413,9 +437,7 @@ static bool bsr_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D) {
 
 // true when the block-sparse tensor-core kernel can run this operator: one m-tile fits in shared memory and the batch
 // rows can be described by a TMA tensor map (row pitch N*8 bytes must be a multiple of 16)
-bool bsr_available(const sbp_ctx* ctx, const sbp_op* op) {
-    return op->d_bsr_val != nullptr && op->N % 2 == 0 && bsr_fits(ctx, op, 1, 0);
-}
+bool bsr_available(const sbp_ctx* ctx, const sbp_op* op) { return op->d_bsr_val != nullptr && bsr_fits(ctx, op, 1, 0); }
 bool bsr_can_run(const sbp_op* op, const double* U) {
     return op->variant == SBP_KERNEL_BSR_DMMA && (reinterpret_cast<uintptr_t>(U) & 15) == 0;
 }
@@ -457,9 +479,9 @@ static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     // the batch as a 2-D tensor [B][N] of doubles; input boxes = kBsrBX nodes x TI instances, output boxes = one quad
     // of rows x the 8*MTW instances of a consumer warp
     CUtensorMap tmap, tmap_out;
-    int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
+    int32_t rc = OUT == 3 ? make_tmap(&tmap, p.U, 2 * p.N, p.B / 2, kBsrBX, TI / 2) : make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
     if (rc) return rc;
-    rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, 8 * MTW) : make_tmap(&tmap_out, p.U, p.N, p.B, kBsrBX, TI);
+    rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, 8 * MTW) : (tmap_out = tmap, SBP_OK);
     if (rc) return rc;
     SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -477,6 +499,7 @@ template <int MTW, int MH>
 static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out) {
 #define SBP_BSR_OUT(S)                                                       \
     switch (out) {                                                           \
+        case 3: return launch_bsr_k<MTW, MH, S, 3>(ctx, p, smem);            \
         case 2: return launch_bsr_k<MTW, MH, S, 2>(ctx, p, smem);            \
         case 1: return launch_bsr_k<MTW, MH, S, 1>(ctx, p, smem);            \
         default: return launch_bsr_k<MTW, MH, S, 0>(ctx, p, smem);           \
@@ -486,6 +509,10 @@ static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int 
     SBP_BSR_OUT(0)
 #undef SBP_BSR_OUT
 }
+
+int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
+                         double beta, const sbp_op* adv, const double* g, int64_t g_stride, const double* colscale,
+                         const Sat1D* sat);
 
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
                    const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat) {
@@ -518,8 +545,28 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         const char* e = getenv("SBP_BSR_OUT");
         forced_out = e ? atoi(e) : 2;
     }
-    const bool aligned = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;  // N is even
-    const int vec = !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;
+    const bool odd = op->N % 2 != 0;
+    const int vec = odd ? 3 : !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
+    if (odd) {
+        // pair-row view [B/2][2N]: an odd last instance has no partner row and takes the scalar kernel
+        if (B % 2) {
+            const long long lastoff = (B - 1) * (long long)op->N;
+            int32_t rc1;
+            if (sat && sat->enabled) {
+                Sat1D s1 = *sat;
+                s1.bc = sat->bc + (B - 1) * sat->bc_stride;
+                rc1 = launch_sparse_ex(ctx, op, dU + lastoff, U + lastoff, 1, alpha, beta, nullptr, nullptr, 0, nullptr, &s1);
+            } else {
+                rc1 = launch_sparse(ctx, op, dU + lastoff, U + lastoff, 1, alpha, beta, adv,
+                                    g ? g + (B - 1) * g_stride : nullptr, g_stride, nullptr);
+            }
+            if (rc1) return rc1;
+            B -= 1;
+            if (B == 0) return SBP_OK;
+        }
+    }
+    p.B = B;
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller
     // tiles so that every SM gets work.  SBP_BSR_MT / SBP_BSR_DEPTH override (tuning).
