@@ -270,7 +270,7 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
     try:  # config 1 batched: banded 1D FD-SBP operator N = 101 (examples/RBF_FSBP_advection.jl sizes), RHS with SATs
         N, B = 101, 1 << 19
         D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
-        D1.storage = "dense"  # odd N: smem-resident DMMA kernel with band skipping (the TMA kernel needs even N)
+        D1.storage = "sparse"  # block-sparse DMMA kernel (odd N: pair-row view of the batch)
         semi1 = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False,
                                                                        lambda t: 0.3, lambda t: 0.0)
         U = torch.rand((B, N), dtype=torch.float64, device=dev) * 2 - 1

@@ -566,3 +566,52 @@ def test_config5_sized_dense_gemm_checksum(ctx):
     assert np.max(np.abs(lhs - rhs) / scale) <= 1e-13
     sub = du.to_host()[:64]
     assert rel_err(sub, O.apply_batch(Dm, U[:64])) <= TOL
+
+
+# ---- committed golden fixtures (tests/golden/hotpath_golden.npz, generated by tests/golden/make_golden.py) ---------
+def test_golden_fixtures(ctx):
+    import os
+
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.npz"))
+    # (1) LGL N = 16 apply, alpha/beta form, energy
+    D = S.PolynomialBasesDerivativeOperator(S.LobattoLegendre, -2.0, 1.4, 16)
+    u = ctx.upload(gold["lgl16_U"])
+    assert rel_err((D * u).to_host(), gold["lgl16_dU"]) <= 1e-11  # independent operator constructions: 1e-11
+    y = ctx.upload(gold["lgl16_Y0"])
+    S.mul_(y, D, u, -1.5, 0.25)
+    assert rel_err(y.to_host(), gold["lgl16_dU_axpby"]) <= 1e-11
+    assert np.max(np.abs(S.integrate(S.abs2, u, D) - gold["lgl16_energy"]) / gold["lgl16_energy"]) <= TOL
+    # (2) banded operators, even and odd N, dense and sparse kernels
+    for N in (20, 21):
+        for storage in ("dense", "sparse"):
+            Dm = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+            Dm.storage = storage
+            assert rel_err((Dm * ctx.upload(gold[f"mn4_{N}_U"])).to_host(), gold[f"mn4_{N}_dU"]) <= TOL
+    # (3) sub-cell operator table with fused energy
+    ops, _ = _subcell_table()
+    table = S.OperatorTable(ops)
+    u = ctx.upload(gold["subcell_U"])
+    du = S.DeviceBatch.empty(ctx, 8, 16)
+    _, E, _ = table.mul_(du, u, energy=True, energy_sum=True)
+    assert rel_err(du.to_host(), gold["subcell_dU"]) <= 1e-11
+    assert np.max(np.abs(E - gold["subcell_energy"]) / gold["subcell_energy"]) <= 1e-11
+    # (4) 2D advection RHS + quantities, both storages
+    D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, 8))
+    a, t = (1.0, -0.5), 0.37
+    g = lambda x, tt: np.exp(-30 * ((x[0] - a[0] * tt) ** 2 + (x[1] - a[1] * tt) ** 2)) + 0.1 * np.sin(3 * x[0] - x[1] + tt)
+    for storage in ("sparse", "dense"):
+        semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D2, a, g, storage=storage)
+        u, du = ctx.upload(gold["adv2d_U"]), S.DeviceBatch.empty(ctx, 3, 64)
+        semi(du, u, None, t)
+        assert rel_err(du.to_host(), gold["adv2d_dU"]) <= TOL
+        Q = S.analyze_quantities(semi, du, u, None, t)
+        assert np.max(np.abs(Q - gold["adv2d_quantities"])) <= 1e-11 * max(1.0, np.max(np.abs(gold["adv2d_quantities"])))
+    # (5) 1D advection RHS with SATs
+    D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, 21)
+    D1.storage = "sparse"
+    semi1 = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False,
+                                                                   lambda tt: np.tanh(50 * (-tt - 0.1)),
+                                                                   lambda tt: 0.3 * np.cos(tt))
+    u, du = ctx.upload(gold["adv1d_U"]), S.DeviceBatch.empty(ctx, 3, 21)
+    semi1(du, u, None, 0.2)
+    assert rel_err(du.to_host(), gold["adv1d_dU"]) <= TOL

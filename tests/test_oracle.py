@@ -310,3 +310,48 @@ def test_c_port_matches_numpy_oracle():
     rp, ci, va = CO.dense_to_csr(semi.A)
     assert np.allclose(CO.apply_csr(rp, ci, va, U), U @ semi.A.T, rtol=1e-13, atol=1e-13)
     assert CO.max_threads() >= 1
+
+
+# ---- golden fixtures (tests/golden) --------------------------------------------------------------------------------
+def _golden_dir():
+    import os
+
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reference_known_answers_moments_boundary():
+    """The literal numbers of the reference's 'moments' test item (test/test_unit.jl:15-41): boundary moments
+    M[k,l] = sum_i f_k f_l(x_i) * weights_boundary[i] * normals[i][dim] (src/utils/moments.jl:13-61).  Pins the oracle's
+    boundary data (4th-order MN2004 norm as boundary weights, normals, duplicated corners)."""
+    import json
+    import os
+
+    ref = json.load(open(os.path.join(_golden_dir(), "reference_known_answers.json")))
+    o = ref["operator"]
+    D = O.mattsson_nordstrom_2004(o["accuracy_order"], o["xmin"], o["xmax"], o["N"])
+    x = D.grid
+    f1 = [np.ones_like, lambda v: v, lambda v: v**2, np.exp, np.sin]
+    M = np.array([[fk(x)[-1] * fl(x)[-1] - fk(x)[0] * fl(x)[0] for fl in f1] for fk in f1])
+    assert np.array_equal(M, np.array(ref["moments_boundary_1d"]["M"]))  # the reference asserts == here
+    D2 = O.tensor_product_operator_2D(D)
+    X = D2.nodes[np.asarray(D2.boundary_indices)]
+    f2 = [lambda p: np.ones(len(p)), lambda p: p[:, 0], lambda p: p[:, 1], lambda p: np.sin(p[:, 0] * p[:, 1])]
+    for dim, key in ((0, "M_x"), (1, "M_y")):
+        wn = O.weights_boundary_scaled(D2, dim)
+        Md = np.array([[np.sum(fk(X) * fl(X) * wn) for fl in f2] for fk in f2])
+        assert np.allclose(Md, np.array(ref["moments_boundary_2d"][key]), rtol=1e-14, atol=1e-14)  # reference: .≈
+
+
+def test_oracle_reproduces_golden_fixture():
+    """hotpath_golden.npz is regenerated bit for bit by tests/golden/make_golden.py (the oracle has not drifted)."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(_golden_dir(), "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    new = mod.build()
+    old = np.load(os.path.join(_golden_dir(), "hotpath_golden.npz"))
+    assert sorted(new) == sorted(old.files)
+    for k in old.files:
+        assert np.allclose(new[k], old[k], rtol=1e-14, atol=1e-14), k
