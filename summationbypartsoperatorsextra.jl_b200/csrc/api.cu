@@ -319,8 +319,33 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
 //  * CHUNKS of 4 row blocks define the window of TMA boxes (kBsrBX nodes) [blo_c, bhi_c) that must be resident while
 //    the chunk is multiplied; nbox[d] is the ring size that lets the boxes of the next d chunks stream in meanwhile
 //    (the stream continues across the tiles of a CTA, nbt boxes per tile).
-static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, const std::vector<int>& col,
-                         const std::vector<double>& val) {
+static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, const std::vector<int>& col1,
+                         const std::vector<double>& val1) {
+    // Odd N: the rows of the batch are not multiples of 16 bytes, which the TMA needs (global strides AND box origins:
+    // an odd innermost coordinate is an illegal instruction, tools/tma_coord_test.cu).  The batch is then read as
+    // [B/2][2N] (two instances per tensor row) and multiplied by the block-diagonal operator diag(D, D) of size 2N: the
+    // even-N data path runs unchanged, row blocks that straddle the two halves are ordinary sparse row blocks.
+    const bool paired = (N1 & 1) != 0;
+    const int N = paired ? 2 * N1 : N1;
+    std::vector<int> rowptr2, col2;
+    std::vector<double> val2;
+    if (paired) {
+        rowptr2.assign(N + 1, 0);
+        col2.reserve(2 * col1.size());
+        val2.reserve(2 * val1.size());
+        for (int h = 0; h < 2; h++)
+            for (int r = 0; r < N1; r++) {
+                for (int j = rowptr1[r]; j < rowptr1[r + 1]; j++) {
+                    col2.push_back(col1[j] + h * N1);
+                    val2.push_back(val1[j]);
+                }
+                rowptr2[h * N1 + r + 1] = (int)col2.size();
+            }
+    }
+    const std::vector<int>& rowptr = paired ? rowptr2 : rowptr1;
+    const std::vector<int>& col = paired ? col2 : col1;
+    const std::vector<double>& val = paired ? val2 : val1;
+    op->bsr_N = N;
     constexpr int CH = kBsrCH;
     constexpr int BX = kBsrBX;
     const int nq = (N + 3) / 4;
@@ -380,21 +405,16 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     }
     const int nrb = (int)rows.size() / 2, nch = (nrb + CH - 1) / CH;
     auto block_row = [&](int rb, int g) { return (g < 4 ? rows[2 * rb] : rows[2 * rb + 1] - 4) + g; };
-    // odd N: the batch is read through a pair-row view whose odd instances are shifted by one node (see bsr.cu), so a
-    // fragment carries two sets of ring codes: columns c (even instances) and c + 1 (odd instances)
-    const int PS = (N & 1) ? 8 : 4;
+    constexpr int PS = 4;  // ring codes per fragment
     std::vector<int> rbf(nrb + 1, 0), pos;
     std::vector<double> frag;
     std::vector<int> cmin(nch, N), cmax(nch, 0);
-    op->bsr_rb_first = op->bsr_rb_last = 0;
     for (int rb = 0; rb < nrb; rb++) {
         std::vector<int> u;
         const int c = rb / CH;
         for (int g = 0; g < 8; g++) {
             const int r = block_row(rb, g);
             if (r >= N) continue;
-            if (r == 0) op->bsr_rb_first = rb;
-            if (r == N - 1) op->bsr_rb_last = rb;
             for (int j = rowptr[r]; j < rowptr[r + 1]; j++) u.push_back(col[j]);
             // the block's own rows are part of the chunk's window (the SAT epilogues read u_j from the ring)
             cmin[c] = std::min(cmin[c], r);
@@ -427,7 +447,6 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
                 for (int t = 0; t < 4; t++) {
                     const int k = cols[t < taken ? t : 0];
                     pos[(f0 + f) * PS + t] = u[k];
-                    if (PS == 8) pos[(f0 + f) * PS + 4 + t] = u[k] + 1;
                     if (t < taken) where[k] = 4 * f + t;
                 }
             }
@@ -451,7 +470,7 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     std::vector<int> blo(nch), bhi(nch);
     for (int c = 0, m = 0; c < nch; c++) {
         m = std::max(m, cmax[c]);
-        bhi[c] = (m + (PS == 8 ? 1 : 0) + BX - 1) / BX;
+        bhi[c] = (m + BX - 1) / BX;
     }
     for (int c = nch - 1, m = N; c >= 0; c--) {
         m = std::min(m, cmin[c]);
@@ -489,6 +508,29 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
         }
         op->bsr_nbox[d] = (int)need;
     }
+    // per-row-block records read by the consumer warps, one array per pipeline depth d (the ring size differs):
+    // {first fragment relative to the chunk, fragments, first row of quad A, of quad B | ring slot of the chunk's lowest
+    // box (blo % nbox[d]), blo, 0, 0}; padded to whole chunks with inactive records (rows >= N, no fragments)
+    std::vector<int> item(4 * (size_t)nch * CH * 8, 0);
+    for (int d = 0; d < 4; d++)
+        for (int rb = 0; rb < nch * CH; rb++) {
+            int* e = &item[((size_t)d * nch * CH + rb) * 8];
+            if (rb < nrb) {
+                for (int k = 0; k < 4; k++) e[k] = rbmeta[4 * rb + k];
+                e[4] = blo[rb / CH] % op->bsr_nbox[d];
+                e[5] = blo[rb / CH];
+                // rows of the block that carry a 1D SAT: bit k = block row k is node 0 of its instance, bit 8 + k = node N1 - 1
+                for (int k = 0; k < 8; k++) {
+                    const int r = block_row(rb, k);
+                    if (r >= N) continue;
+                    const int n = r % N1;
+                    if (n == 0) e[6] |= 1 << k;
+                    if (n == N1 - 1) e[6] |= 1 << (8 + k);
+                }
+            } else {
+                e[2] = 1 << 30, e[3] = (1 << 30) + 4;
+            }
+        }
     op->bsr_maxf = maxf;
     op->bsr_nrb = nrb;
     op->bsr_rows = rows;
@@ -501,6 +543,7 @@ static int32_t build_bsr(sbp_op* op, int N, const std::vector<int>& rowptr, cons
     if (!rc) rc = upload(&op->d_bsr_pos, pos);
     if (!rc) rc = upload(&op->d_bsr_rbmeta, rbmeta);
     if (!rc) rc = upload(&op->d_bsr_chmeta, chmeta);
+    if (!rc) rc = upload(&op->d_bsr_item, item);
     return rc;
 }
 
@@ -693,7 +736,7 @@ int32_t sbp_op_destroy(sbp_op* op) {
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
                     op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
-                    op->d_rb_bdiag};
+                    op->d_rb_bdiag,  op->d_bsr_item};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -817,11 +860,12 @@ int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h
     if (!rc) rc = upload(&op->d_mode, mode);
     if (!rc && A->variant == SBP_KERNEL_BSR_DMMA) {
         // b_j of every block row in block order (quad A rows 0..3, quad B rows 4..7); 0 where no SAT applies
-        std::vector<double> rbb(8 * (size_t)A->bsr_nrb, 0.0);
+        const size_t nrb_pad = (size_t)((A->bsr_nrb + kBsrCH - 1) / kBsrCH) * kBsrCH;  // whole chunks: read without a guard
+        std::vector<double> rbb(8 * nrb_pad, 0.0);
         for (int rb = 0; rb < A->bsr_nrb; rb++)
             for (int r = 0; r < 8; r++) {
                 const int i = (r < 4 ? A->bsr_rows[2 * rb] : A->bsr_rows[2 * rb + 1] - 4) + r;
-                if (i < N && h_mode[i] == 1) rbb[8 * (size_t)rb + r] = h_b[i];
+                if (i < A->bsr_N && h_mode[i % N] == 1) rbb[8 * (size_t)rb + r] = h_b[i % N];  // bsr_N = 2N: instance pairs
             }
         rc = upload(&op->d_rb_bdiag, rbb);
     }

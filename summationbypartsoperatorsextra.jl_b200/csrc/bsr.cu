@@ -42,6 +42,16 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// -DSBP_BSR_TRACE: per-warp cycle accounting of the consumer phases (clock64 stamps; block 0 prints its totals)
+#ifdef SBP_BSR_TRACE
+#include <cstdio>
+#define TR_DECL long long tr_t = clock64(), tr_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; int tr_items = 0;
+#define TR(k) { const long long tr_n = clock64(); tr_acc[k] += tr_n - tr_t; tr_t = tr_n; }
+#else
+#define TR_DECL
+#define TR(k)
+#endif
+
 namespace sbp {
 
 constexpr int kBsrMaxStages = 4;
@@ -53,12 +63,13 @@ struct BsrParams {
     double* __restrict__ dU;
     const double* __restrict__ val;   // [fragment][32]
     const int* __restrict__ pos;      // [fragment][4]  (box - boxlo[chunk]) << 8 | node % kBsrBX
+    const int4* __restrict__ item;    // [nch * kBsrCH][2] consumer records for this launch's pipeline depth (api.cu build_bsr)
     const int4* __restrict__ rbmeta;  // [nrb] {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
     const int4* __restrict__ chmeta;  // [nch] {first fragment, end fragment, boxlo, boxhi}: boxes [0, boxhi) of the tile are
                                       // resident once the chunk has been staged; no later chunk touches a box below boxlo
     int N, nrb, nch, nbox, nbt, maxf, nst;  // nbox ring slots, nbt boxes per tile, nst pipeline stages
-    int rb_first, rb_last;            // row blocks holding row 0 and row N-1 (1D SATs)
-    long long B;
+    int Nh;                           // nodes per instance: N, or N/2 when a tensor row holds an instance PAIR (odd Nh)
+    long long B;                      // tensor rows (instances, or instance pairs)
     double alpha, beta;
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
     const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows
@@ -91,18 +102,21 @@ template <int MTW, int MH, int SAT, int OUT>
 __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     k_bsr(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
-    // PAIR (OUT == 3, odd N): the rows of the batch are not 16-byte multiples, so the batch is viewed as [B/2][2N]
-    // (two instances per tensor row); a box is fetched as two sub-boxes {nodes, TI/2 rows} at x and x + N, and lane g of
-    // an m-tile owns instance 8mt + 2(g&3) + (g>>2): a half-warp gathers 4 rows of ONE sub-box (conflict free)
-    constexpr bool PAIR = OUT == 3;
-    constexpr int MTS = PAIR ? 4 * kBsrBX : 8 * kBsrBX;  // smem distance between the m-tiles of a lane
-    // TMA box origins must be 16-byte aligned: the odd instances (which start at the odd element N of a pair row) are
-    // fetched from x + N - 1, i.e. shifted by one node; their ring codes are those of column + 1 (second half of the
-    // fragment's code array, PS = 8 codes per fragment)
-    constexpr int PS = PAIR ? 8 : 4;
+    // Odd N: a tensor row is an instance PAIR (2N doubles, a multiple of 16 bytes) and the operator image is that of
+    // diag(D, D) (api.cu build_bsr): nothing in the data path changes, only the SAT terms map a row of the pair back to
+    // (instance, node) with p.Nh.
+    constexpr int MTS = 8 * kBsrBX;  // smem distance between the m-tiles of a lane
+    constexpr int PS = 4;            // ring codes per fragment
     constexpr int MT = MTW;
     constexpr int TI = 8 * MTW * MH;
     constexpr int CONS = kBsrGroups * kBsrCH * MH;  // consumer warps
+    // PING (-DSBP_BSR_PING=1, off by default): the KW consumer warps that share an SM sub-partition (warp % 4) pass a token
+    // through named barriers so that their DMMA chains are mutually exclusive (one warp's scalar prologue/epilogue would
+    // hide behind the other's chain).  Measured on B200: the token is never contended (28 cycles of waiting per item) and
+    // the chain of a warp takes ~30 cycles per DMMA with or without it -- the chain is bound by its own operand
+    // latencies, not by the pipe -- so the exchange only costs (config 3: 0.338 ms with, 0.325 ms without).
+    constexpr int KW = CONS / 4;
+    constexpr bool PING = SBP_BSR_PING && kBsrGroups == 1 && CONS % 4 == 0 && KW >= 2 && KW <= 3;
     constexpr int BX = kBsrBX;
     constexpr int BOX = TI * BX;  // doubles per box
     extern __shared__ __align__(128) double smem[];
@@ -158,14 +172,8 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                             asm volatile(
                                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
                                 "{%2, %3}], [%4];\n" ::"r"(dst),
-                                "l"(&tmap), "r"(x), "r"(PAIR ? b0 / 2 : b0), "r"(bar)
+                                "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
                                 : "memory");
-                            if (PAIR)  // the odd instances of the pair rows
-                                asm volatile(
-                                    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], "
-                                    "[%1, {%2, %3}], [%4];\n" ::"r"(dst + (uint32_t)(BOX * 4)),
-                                    "l"(&tmap), "r"(x + N - 1), "r"(b0 / 2), "r"(bar)
-                                    : "memory");
                             if (++slot == nbox) slot = 0;
                         }
                     } else {
@@ -201,28 +209,26 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     const int g = lane >> 2, t = lane & 3;
     const int grp = warp / (kBsrCH * MH), slotw = (warp / MH) % kBsrCH, mh = warp % MH;
     const int i0 = mh * 8 * MTW;  // first instance (tile row) of this warp
-    // local instance of lane g in m-tile mt, and where an instance's row lives inside a box
-    auto inst_of = [&](int mt) { return PAIR ? 8 * mt + 2 * (g & 3) + (g >> 2) : 8 * mt + g; };
-    auto inst_off = [&](int il) { return PAIR ? (il & 1) * (TI / 2) * BX + (il >> 1) * BX : il * BX; };
-    const double* su = s_u + inst_off(i0 + inst_of(0));
+    const double* su = s_u + (i0 + g) * BX;  // lane g owns tensor row 8 mt + g of m-tile mt
+    // (instance, node) of row r of a tensor row: r itself, or (half, r - half * Nh) for instance pairs
+    const int Nh = p.Nh;
+    const bool paired = Nh != N;
 
-    // per-item operator constants (independent of the tile), fetched one item ahead with independent loads
+    // per-item operator constants (independent of the tile): one 32-byte record per row block, prepared on the host for
+    // this launch's pipeline depth and fetched one item ahead (two independent 16-byte loads + the SAT coefficients)
     struct Meta {
         int4 rb;       // {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
-        int blo;       // lowest box of the chunk's window
+        int4 x;        // {ring slot of the chunk's lowest box, lowest box of the chunk's window, -, -}
         double2 sb;    // SAT coefficients of the lane's two rows (0: no SAT)
     };
+    const int4* const items = p.item + 2 * slotw;
+    const double2* const sbs = reinterpret_cast<const double2*>(p.rb_bdiag) + 4 * slotw + t;
     auto load_meta = [&](int c) {
         Meta m;
-        const int rb = c * kBsrCH + slotw;
-        m.rb = make_int4(0, 0, N, N + 4);
-        m.blo = 0;
+        m.rb = __ldg(items + c * (2 * kBsrCH));
+        m.x = __ldg(items + c * (2 * kBsrCH) + 1);
         m.sb = make_double2(0.0, 0.0);
-        if (rb < p.nrb) {
-            m.rb = __ldg(p.rbmeta + rb);
-            m.blo = __ldg(p.chmeta + c).z;
-            if (SAT == 1) m.sb = __ldg(reinterpret_cast<const double2*>(p.rb_bdiag) + rb * 4 + t);
-        }
+        if (SAT == 1) m.sb = __ldg(sbs + c * (4 * kBsrCH));
         return m;
     };
 
@@ -231,19 +237,32 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     // requested together with earlier items (of the other group), so their arrival must have been observed too, and
     // a stage may only be refilled once no warp can still be waiting on its previous phase.
     int c = 0, off = 0, st = 0, round = 0, turn = 0;
-    long long tile = blockIdx.x;
+    int tile = blockIdx.x, b0 = blockIdx.x * TI;  // B < 2^31 (checked by the launcher)
+    const int ntl = (int)ntiles, tstep = gridDim.x * TI, Bi = (int)p.B;
     Meta m = load_meta(grp % p.nch);
+    // tensor-pipe token of this warp's scheduler: barrier id (1 + KW * scheduler + k) = "warp k may multiply"
+    const int pp_me = 1 + KW * (warp & 3) + (warp >> 2);
+    const int pp_next = 1 + KW * (warp & 3) + ((warp >> 2) + 1 == KW ? 0 : (warp >> 2) + 1);
+    if (PING && (warp >> 2) == KW - 1) named_bar_arrive(pp_next, 64);  // the first turn belongs to warp k = 0
     auto next_item = [&]() {
         if (++c == p.nch) {
             c = 0;
             tile += gridDim.x;
+            b0 += tstep;
             off += stepb;
             if (off >= nbox) off -= nbox;
         }
         if (++st == nst) st = 0, round++;
         if (++turn == kBsrGroups) turn = 0;
     };
-    for (; tile < ntiles; next_item()) {
+    // 1D SATs: reciprocal boundary weights and, when the boundary data are shared by the batch, the data themselves
+    double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0;
+    if (SAT == 2) {
+        sat_iw0 = 1.0 / p.sat.w0, sat_iwN = 1.0 / p.sat.wN;
+        if (p.sat.bc_stride == 0) sat_lb = __ldg(p.sat.bc), sat_rb = __ldg(p.sat.bc + 1);
+    }
+    TR_DECL
+    for (; tile < ntl; next_item()) {
         if (turn != grp) {
             mbar_wait(&bar_full[st], round & 1);
             __syncwarp();
@@ -253,17 +272,21 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
         int cn = c + kBsrGroups;  // chunk of this warp's next item: its operator constants are prefetched now
         while (cn >= p.nch) cn -= p.nch;
         const Meta mn = load_meta(cn);
+        TR(0)  // next_item + metadata prefetch
 
-        const long long b0 = tile * TI;
-        const int nb = (p.B - b0) < TI ? (int)(p.B - b0) : TI;
+        const int nb = (Bi - b0) < TI ? Bi - b0 : TI;
         const int rb = c * kBsrCH + slotw;
-        const bool active = rb < p.nrb;
         const int4 rbm = m.rb;
+        const bool active = rbm.z < N;  // padding records of the last chunk carry rows >= N
         const double2 sb = m.sb;
         const int r0 = (t < 2 ? rbm.z : rbm.w - 4) + 2 * t;  // lane owns rows r0, r0 + 1 (pair t of the block)
-        const int blo = m.blo, nf = rbm.y;
-        const int mask = (SAT == 1) ? ((sb.x != 0.0 ? 1 : 0) | (sb.y != 0.0 ? 2 : 0)) : 0;
-        int cb = blo % nbox + off;  // ring slot of box blo in this tile
+        const int blo = m.x.y, nf = rbm.y;
+        // (half, node) of the lane's two rows: for instance pairs row r >= Nh is node r - Nh of the odd instance
+        const int h0 = (paired && r0 >= Nh) ? 1 : 0, h1 = (paired && r0 + 1 >= Nh) ? 1 : 0;
+        const int n0 = r0 - h0 * Nh, n1 = r0 + 1 - h1 * Nh;
+        // b_j != 0 tested on the bit pattern (no trip through the FP64 pipe)
+        const int mask = (SAT == 1) ? (((__double_as_longlong(sb.x) << 1) != 0 ? 1 : 0) | ((__double_as_longlong(sb.y) << 1) != 0 ? 2 : 0)) : 0;
+        int cb = m.x.x + off;  // ring slot of box blo in this tile
         if (cb >= nbox) cb -= nbox;
         // element offset of (box-relative, column) code q inside the ring
         auto ring_off = [&](int q) {
@@ -278,27 +301,39 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
         // boundary data shared by the batch (g_stride == 0): requested before the wait, consumed in the epilogue
         double gs0 = 0.0, gs1 = 0.0;
         if (SAT == 1 && mask && p.g_stride == 0) {
-            if (mask & 1) gs0 = __ldg(p.g + r0);
-            if (mask & 2) gs1 = __ldg(p.g + r0 + 1);
+            if (mask & 1) gs0 = __ldg(p.g + n0);
+            if (mask & 2) gs1 = __ldg(p.g + n1);
         }
+        TR(1)  // tile/row/ring constants, boundary data
         mbar_wait(&bar_full[st], round & 1);
+        TR(2)  // wait for the stage
         {
             const double* sv = s_val + (size_t)st * p.maxf * 32 + (size_t)rbm.x * 32 + lane;
-            const int* sp = s_pos + (size_t)st * p.maxf * PS + rbm.x * PS + (PAIR ? 4 * (g >> 2) : 0) + t;
+            const int* sp = s_pos + (size_t)st * p.maxf * PS + rbm.x * PS + t;
             const int nfe = active ? nf : 0;
             // software pipeline: ring offsets two fragments ahead, operands one fragment ahead
+            // alpha == -1 (every RHS call): the sign is folded into the operator fragment as it is loaded (one integer
+            // XOR per fragment, issued under the DMMA chain) instead of 2*MT FP64 negations on the epilogue's critical path
+            const int sgn = alpha_m1 ? (int)0x80000000u : 0;
+            auto ldb = [&](const double* q) {
+                const double v = *q;
+                return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v));
+            };
             double b_cur = 0.0, a_cur[MT];
             int o_nxt = 0;
             if (nfe > 0) {
-                b_cur = sv[0];
+                b_cur = ldb(sv);
                 const int o0 = ring_off(sp[0]);
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) a_cur[mt] = su[mt * MTS + o0];
                 o_nxt = ring_off(sp[nfe > 1 ? PS : 0]);
             }
+            TR(3)  // operand pointers, first operands
+            if (PING) named_bar_sync(pp_me, 64);  // first operands are in flight; wait for the pipe
+            TR(4)  // wait for the pipe token
             if (nfe > 0) {
                 for (int f = 1; f < nfe; f++) {
-                    const double b_nxt = sv[f * 32];
+                    const double b_nxt = ldb(sv + f * 32);
                     double a_nxt[MT];
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) a_nxt[mt] = su[mt * MTS + o_nxt];
@@ -312,74 +347,93 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][0], acc[mt][1], a_cur[mt], b_cur);
             }
+            TR(5)  // DMMA chain
+            if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the next warp of this scheduler may start
         }
         if (active) {
-            // acc <- alpha * acc (the RHS calls with alpha = -1: a sign flip instead of FP64 multiplies), then the SAT
+            // acc <- alpha * acc (alpha = -1 was folded into the fragments), then the SAT
             // terms are added in place while the stage is still held (they read the own-row values from the ring)
+            if (!alpha_m1) {
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                if (alpha_m1) {
-                    acc[mt][0] = -acc[mt][0], acc[mt][1] = -acc[mt][1];
-                } else {
-                    acc[mt][0] *= p.alpha, acc[mt][1] *= p.alpha;
-                }
+                for (int mt = 0; mt < MT; mt++) acc[mt][0] *= p.alpha, acc[mt][1] *= p.alpha;
             }
             if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
-                const int n0 = r0 + (PAIR ? (g >> 2) : 0);  // odd instances of a pair row are stored one node later
-                const int q0 = n0 / BX, q1 = (n0 + 1) / BX;
-                const int o0 = ring_off(((q0 - blo) << 8) | (n0 - q0 * BX));
-                const int o1 = ring_off(((q1 - blo) << 8) | (n0 + 1 - q1 * BX));
+                const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
+                const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
+                const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     if (p.g_stride != 0) {  // per-instance boundary data
-                        const int il = i0 + inst_of(mt);
-                        const double* gp = p.g + (b0 + (il < nb ? il : 0)) * p.g_stride + r0;
-                        if (mask & 1) gs0 = __ldg(gp);
-                        if (mask & 2) gs1 = __ldg(gp + 1);
+                        const int il = i0 + 8 * mt + g;
+                        const long long row = b0 + (il < nb ? il : 0);
+                        if (mask & 1) gs0 = __ldg(p.g + (paired ? 2 * row + h0 : row) * p.g_stride + n0);
+                        if (mask & 2) gs1 = __ldg(p.g + (paired ? 2 * row + h1 : row) * p.g_stride + n1);
                     }
                     if (mask & 1) acc[mt][0] += sb.x * (su[mt * MTS + o0] - gs0);
                     if (mask & 2) acc[mt][1] += sb.y * (su[mt * MTS + o1] - gs1);
                 }
             }
-            if (SAT == 2 && (rb == p.rb_first || rb == p.rb_last)) {
-                // 1D SATs at rows 0 and N-1: one division per instance.  Lane l evaluates them for the warp's
-                // instances l (and l + 32) in parallel; the owners of the two rows fetch them by shuffle.
-                // code of a node inside the ring, for an instance of the given parity (odd: stored one node later)
-                auto node_off = [&](int n, int par) {
-                    const int nn = n + (PAIR ? par : 0), q = nn / BX;
-                    return ring_off(((q - blo) << 8) | (nn - q * BX));
-                };
-                double sl[(8 * MTW + 31) / 32], sr[(8 * MTW + 31) / 32];
+            if (SAT == 2 && m.x.z != 0) {
+                // 1D SATs at nodes 0 and Nh-1 of every instance (the record flags the block rows that carry one).  One
+                // division per instance: lane l evaluates the term for the warp's tensor rows l (and l + 32) in parallel,
+                // the lane that owns the row fetches it by shuffle.
+                const int flags = m.x.z;
+#pragma unroll 1
+                for (int k = 0; k < 8; k++) {
+                    const bool left = (flags >> k) & 1, right = (flags >> (8 + k)) & 1;
+                    if (!(left | right)) continue;
+                    const int r = (k < 4 ? rbm.z : rbm.w - 4) + k;
+                    const int h = (paired && r >= Nh) ? 1 : 0, q = r / BX;
+                    const int o = ring_off(((q - blo) << 8) | (r - q * BX));
+                    double sv2[(8 * MTW + 31) / 32];
 #pragma unroll
-                for (int k = 0; k < (8 * MTW + 31) / 32; k++) {
-                    const int il = lane + 32 * k;  // instance within the warp's share
-                    sl[k] = sr[k] = 0.0;
-                    if (il < 8 * MTW && i0 + il < nb) {
-                        const long long inst = b0 + i0 + il;
-                        const double* up = s_u + inst_off(i0 + il);
-                        if (rb == p.rb_first) sl[k] = sat1d_left(p.sat, inst, p.sat.a0 * up[node_off(0, il & 1)]);
-                        if (rb == p.rb_last) sr[k] = sat1d_right(p.sat, inst, p.sat.aN * up[node_off(N - 1, il & 1)]);
+                    for (int kk = 0; kk < (8 * MTW + 31) / 32; kk++) {
+                        const int il = lane + 32 * kk;  // tensor row within the warp's share
+                        sv2[kk] = 0.0;
+                        if (il < 8 * MTW && i0 + il < nb) {
+                            const long long row = (long long)b0 + i0 + il, inst = paired ? 2 * row + h : row;
+                            const double u = s_u[(i0 + il) * BX + o];
+                            double lb = sat_lb, rbv = sat_rb;
+                            if (p.sat.bc_stride != 0) {  // per-instance boundary data
+                                if (left) lb = __ldg(p.sat.bc + inst * p.sat.bc_stride);
+                                if (right) rbv = __ldg(p.sat.bc + inst * p.sat.bc_stride + 1);
+                            }
+                            // (f - a u) / w as in sat1d_left/right, with the division replaced by the reciprocal weight
+                            double v = 0.0;
+                            if (left) {
+                                const double t0 = p.sat.a0 * u;
+                                v += ((p.sat.a0 > 0.0 ? p.sat.a0 * lb : t0) - t0) * sat_iw0;
+                            }
+                            if (right) {
+                                const double tN = p.sat.aN * u;
+                                v -= ((p.sat.aN > 0.0 ? tN : p.sat.aN * rbv) - tN) * sat_iwN;
+                            }
+                            sv2[kk] = v;
+                        }
                     }
-                }
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    const int il = inst_of(mt);
-                    const double vl = __shfl_sync(0xffffffffu, sl[il >> 5], il & 31);
-                    const double vr = __shfl_sync(0xffffffffu, sr[il >> 5], il & 31);
-                    if (r0 == 0) acc[mt][0] += vl;
-                    if (r0 == N - 1) acc[mt][0] += vr;
-                    if (r0 + 1 == N - 1) acc[mt][1] += vr;
+                    for (int mt = 0; mt < MT; mt++) {
+                        const int il = 8 * mt + g;
+                        const double v = __shfl_sync(0xffffffffu, sv2[il >> 5], il & 31);
+                        if (t == (k >> 1)) {
+                            if (k & 1) acc[mt][1] += v;
+                            else acc[mt][0] += v;
+                        }
+                    }
                 }
             }
         }
+        TR(6)  // scale + SAT
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);  // the stage (and the ring slots behind it) may be refilled
+        TR(7)  // release
         if (OUT == 2) {
             // ---- epilogue through TMA: lane (g,t) deposits rows r0, r0+1 of instance 8mt + g in the warp's staging
             //      buffer; one elected lane stores quad A and quad B as {4 rows x 8*MTW instances} boxes ----
             double* so = s_out + (size_t)warp * (2 * 8 * MTW * 4);
             if (lane == 0) bulk_wait_read<0>();  // the previous boxes of this warp have been read out of the buffer
             __syncwarp();
+            TR(8)  // staging buffer free
             if (active) {
                 double* sq = so + (t >> 1) * (8 * MTW * 4) + g * 4 + (t & 1) * 2;
 #pragma unroll
@@ -387,8 +441,9 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                     *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
                 fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
                 __syncwarp();
+                TR(9)  // results staged
                 if (lane == 0) {
-                    const int y = (int)b0 + i0;
+                    const int y = b0 + i0;
                     if (rbm.z < N) tma_store_2d(&tmap_out, rbm.z, y, so);
                     if (rbm.w < N) tma_store_2d(&tmap_out, rbm.w, y, so + 8 * MTW * 4);
                     bulk_commit();
@@ -398,10 +453,10 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
             // ---- epilogue: lane owns rows r0, r0+1 of instance i0 + 8mt + g ----
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
-                const int il = i0 + inst_of(mt);
+                const int il = i0 + 8 * mt + g;
                 if (il >= nb) continue;
                 double y0 = acc[mt][0], y1 = acc[mt][1];
-                double* yp = p.dU + (b0 + il) * N + r0;
+                double* yp = p.dU + (long long)(b0 + il) * N + r0;
                 if (VEC) {  // N even: row r0 + 1 exists
                     if (p.beta != 0.0) {
                         const double2 o = *reinterpret_cast<const double2*>(yp);
@@ -420,14 +475,27 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
             }
         }
         m = mn;
+        TR(10)  // tensor stores
+#ifdef SBP_BSR_TRACE
+        tr_items++;
+#endif
     }
+#ifdef SBP_BSR_TRACE
+    if (blockIdx.x == 0 && lane == 0)
+        printf("bsr trace warp %d items %d cycles/item: meta %lld consts %lld wait_full %lld first_ops %lld wait_token %lld dmma %lld sat %lld "
+               "release %lld wait_staging %lld stage %lld tma_store %lld\n",
+               warp, tr_items, tr_acc[0] / tr_items, tr_acc[1] / tr_items, tr_acc[2] / tr_items, tr_acc[3] / tr_items,
+               tr_acc[4] / tr_items, tr_acc[5] / tr_items, tr_acc[6] / tr_items, tr_acc[7] / tr_items, tr_acc[8] / tr_items,
+               tr_acc[9] / tr_items, tr_acc[10] / tr_items);
+#endif
+    if (PING && (warp >> 2) == 0) named_bar_sync(pp_me, 64);  // absorb the last token
     if (OUT == 2 && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
 }
 
 static size_t bsr_smem(const sbp_op* op, int MT, int D) {
     const size_t nch = (op->bsr_nrb + kBsrCH - 1) / kBsrCH;
     (void)nch;
-    const size_t ops = ((size_t)(D + 1) * op->bsr_maxf * (32 * 8 + ((op->N & 1) ? 8 : 4) * 4) + 127) & ~(size_t)127;
+    const size_t ops = ((size_t)(D + 1) * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
     const size_t staging = (size_t)kBsrGroups * kBsrCH * 2 * 8 * MT * 4 * 8;  // per consumer warp: 2 quads x instances x 4 rows
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
@@ -479,7 +547,7 @@ static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     // the batch as a 2-D tensor [B][N] of doubles; input boxes = kBsrBX nodes x TI instances, output boxes = one quad
     // of rows x the 8*MTW instances of a consumer warp
     CUtensorMap tmap, tmap_out;
-    int32_t rc = OUT == 3 ? make_tmap(&tmap, p.U, 2 * p.N, p.B / 2, kBsrBX, TI / 2) : make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
+    int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
     if (rc) return rc;
     rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, 8 * MTW) : (tmap_out = tmap, SBP_OK);
     if (rc) return rc;
@@ -499,7 +567,6 @@ template <int MTW, int MH>
 static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out) {
 #define SBP_BSR_OUT(S)                                                       \
     switch (out) {                                                           \
-        case 3: return launch_bsr_k<MTW, MH, S, 3>(ctx, p, smem);            \
         case 2: return launch_bsr_k<MTW, MH, S, 2>(ctx, p, smem);            \
         case 1: return launch_bsr_k<MTW, MH, S, 1>(ctx, p, smem);            \
         default: return launch_bsr_k<MTW, MH, S, 0>(ctx, p, smem);           \
@@ -516,7 +583,7 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
 
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
                    const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat) {
-    SBP_REQUIRE(B < (1ll << 31), SBP_EUNSUPPORTED, "block-sparse kernel: batch size must be < 2^31");
+    SBP_REQUIRE(B < (1ll << 31) - (1 << 20), SBP_EUNSUPPORTED, "block-sparse kernel: batch size must be < 2^31 - 2^20");
     BsrParams p;
     p.U = U;
     p.dU = dU;
@@ -524,12 +591,11 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.pos = op->d_bsr_pos;
     p.rbmeta = reinterpret_cast<const int4*>(op->d_bsr_rbmeta);
     p.chmeta = reinterpret_cast<const int4*>(op->d_bsr_chmeta);
-    p.N = op->N;
+    p.N = op->bsr_N;  // row length of the tensor view: N, or 2N for odd N (instance pairs)
+    p.Nh = op->N;
     p.nrb = op->bsr_nrb;
     p.nch = (p.nrb + kBsrCH - 1) / kBsrCH;
-    p.rb_first = op->bsr_rb_first;
-    p.rb_last = op->bsr_rb_last;
-    p.nbt = (op->N + kBsrBX - 1) / kBsrBX;
+    p.nbt = (op->bsr_N + kBsrBX - 1) / kBsrBX;
     p.maxf = op->bsr_maxf;
     p.B = B;
     p.alpha = alpha * op->scale;
@@ -546,8 +612,8 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         forced_out = e ? atoi(e) : 2;
     }
     const bool aligned = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;
-    const bool odd = op->N % 2 != 0;
-    const int vec = odd ? 3 : !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
+    const bool odd = op->bsr_N != op->N;
+    const int vec = !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
     if (odd) {
         // pair-row view [B/2][2N]: an odd last instance has no partner row and takes the scalar kernel
         if (B % 2) {
@@ -565,6 +631,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
             B -= 1;
             if (B == 0) return SBP_OK;
         }
+        B /= 2;  // tensor rows = instance pairs
     }
     p.B = B;
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
@@ -591,7 +658,12 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
                 bsr_smem(op, MT, D));
     p.nbox = op->bsr_nbox[D];
     p.nst = D + 1;
+    p.item = reinterpret_cast<const int4*>(op->d_bsr_item) + (size_t)D * p.nch * kBsrCH * 2;
     const size_t smem = bsr_smem(op, MT, D);
+    static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "k_bsr: N=%d B=%lld nrb=%d nch=%d frags=%lld maxf=%d MT=%d stages=%d nbox=%d smem=%zu sat=%d out=%d\n", p.N,
+                (long long)B, p.nrb, p.nch, (long long)op->bsr_frags, p.maxf, MT, D + 1, p.nbox, smem, satmode, vec);
     // one consumer warp per row block of the chunk, MT m-tiles each (SBP_BSR_MH=2: two warps per row block, MT/2 each)
     static int forced_mh = -1;
     if (forced_mh < 0) {
@@ -601,6 +673,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     if (forced_mh == 2 && MT >= 2) {
         switch (MT) {
             case 8: return launch_bsr_mt<4, 2>(ctx, p, smem, satmode, vec);
+            case 6: return launch_bsr_mt<3, 2>(ctx, p, smem, satmode, vec);
             case 4: return launch_bsr_mt<2, 2>(ctx, p, smem, satmode, vec);
             default: return launch_bsr_mt<1, 2>(ctx, p, smem, satmode, vec);
         }

@@ -35,6 +35,9 @@ void set_error(const char* fmt, ...);
 #ifndef SBP_BSR_CH
 #define SBP_BSR_CH 8
 #endif
+#ifndef SBP_BSR_PING
+#define SBP_BSR_PING 0  // 1: consumer warps of one scheduler take turns on the FP64 tensor pipe (see bsr.cu; measured: no gain)
+#endif
 #ifndef SBP_BSR_G
 #define SBP_BSR_G 1
 #endif
@@ -101,8 +104,10 @@ struct sbp_op {
     double* d_bsr_val = nullptr;  // [fragment][32] B-operand fragments (row g, column t)
     int* d_bsr_pos = nullptr;     // [fragment][4] (box - boxlo[chunk]) << 8 | column % kBsrBX
     int* d_bsr_rbmeta = nullptr;  // [nrb][4] {first fragment relative to its chunk, fragments, first row of quad A, of quad B}
+    int* d_bsr_item = nullptr;    // [4 depths][nch * kBsrCH][8] per-row-block record of the consumer warps (see build_bsr)
     int* d_bsr_chmeta = nullptr;  // [nch][4] {first fragment, end fragment, lowest box still needed, boxes resident}
-    int bsr_nrb = 0, bsr_rb_first = 0, bsr_rb_last = 0;
+    int bsr_nrb = 0;
+    int bsr_N = 0;                // row length the block-sparse image works on: N, or 2N for odd N (instance pairs, see build_bsr)
     std::vector<int> bsr_rows;    // host copy: first rows of the two quads of every row block (2 * nrb)
     int bsr_nbox[4] = {0, 0, 0, 0};  // ring size (boxes) that allows d chunks of lookahead, d = 0..3
     int bsr_maxf = 0;

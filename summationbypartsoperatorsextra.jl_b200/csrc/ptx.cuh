@@ -105,6 +105,14 @@ __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// named barriers (ids 1..15; 0 is __syncthreads): bar.sync blocks until `count` threads have arrived, bar.arrive does not block
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // streaming global accesses: data touched exactly once -> do not pollute L1, evict-first in L2
 // ---------------------------------------------------------------------------------------------
