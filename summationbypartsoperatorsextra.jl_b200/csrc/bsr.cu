@@ -525,7 +525,8 @@ static PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
-static int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int box_nodes, int box_inst) {
+// 2-D tensor map over a row-major [B][N] array of doubles with boxes of box_nodes x box_inst (also used by dense_gemm.cu)
+int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int box_nodes, int box_inst) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     SBP_REQUIRE(enc != nullptr, SBP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B};
@@ -557,6 +558,7 @@ static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     if (per_sm < 1) per_sm = 1;
     const long long ntiles = (p.B + TI - 1) / TI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
+    if (getenv("SBP_BSR_VERBOSE")) fprintf(stderr, "k_bsr<%d,%d,%d,%d>: %d CTAs/SM, grid %d, %lld tiles\n", MTW, MH, SAT, OUT, per_sm, grid, ntiles);
     kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
