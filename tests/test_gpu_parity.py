@@ -568,6 +568,48 @@ def test_config5_sized_dense_gemm_checksum(ctx):
     assert rel_err(sub, O.apply_batch(Dm, U[:64])) <= TOL
 
 
+# ---- odd N on the block-sparse kernel: instance PAIRS multiplied by diag(D, D) (csrc/api.cu build_bsr) ------------
+@pytest.mark.parametrize("n1", [5, 7, 9])  # N = 25, 49, 81: odd
+@pytest.mark.parametrize("B", [1, 2, 65, 130, 1027])
+def test_rhs_advection2d_odd_N(ctx, n1, B):
+    D = _scattered_mfsbp(n1, seed=3)
+    assert D.N % 2 == 1
+    a = (0.7, -1.0)
+    g = lambda x, t: np.cos(2 * x[0] - x[1] + t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, g, storage="sparse")
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    U = rand_batch(B, D.N, 5)
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, D.N)
+    semi(du, u, None, 0.3)
+    ref = np.stack([semio.rhs(U[b], 0.3) for b in range(B)])
+    assert rel_err(du.to_host(), ref) <= TOL
+    # per-instance boundary data: every instance of a pair reads its own row of g
+    G = rand_batch(B, D.N, 6)
+    semi(du, u, None, 0.0, g=ctx.upload(G))
+    out = du.to_host()
+    for b in sorted({0, 1, B // 2, B - 2, B - 1} & set(range(B))):
+        semio.bc = lambda node, t, b=b: G[b, int(np.argmin(np.sum((D.grid - node) ** 2, axis=1)))]
+        assert rel_err(out[b], semio.rhs(U[b], 0.0)) <= TOL
+
+
+@pytest.mark.parametrize("N", [21, 101, 103])
+@pytest.mark.parametrize("B", [1, 2, 77, 1030])
+def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B):
+    D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    D.storage = "sparse"
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    for speed in (1.0, -0.8):
+        semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, lambda x: speed, False,
+                                                                       lambda t: 0.0, lambda t: 0.0)
+        U, BC = rand_batch(B, N, 12), rand_batch(B, 2, 13)
+        u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, B, N)
+        semi(du, u, None, 0.0, bc=ctx.upload(BC))
+        out = du.to_host()
+        for b in sorted({0, 1, B // 2, B - 2, B - 1} & set(range(B))):
+            semio = O.AdvectionSemi1D(Do, lambda x: speed, lambda t, b=b: BC[b, 0], lambda t, b=b: BC[b, 1])
+            assert rel_err(out[b], semio.rhs(U[b], 0.0)) <= TOL
+
+
 # ---- committed golden fixtures (tests/golden/hotpath_golden.npz, generated by tests/golden/make_golden.py) ---------
 def test_golden_fixtures(ctx):
     import os

@@ -1,7 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for v in -2 0; do SBP_GEMM_VARIANT=$v python tools/time_config.py --workload config5 --steps 10 --tag gemm$v 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: print(l.strip()[:200]); continue
-    print(d['tag'], d['ms_median'], 'ms', 2*d['N']*d['N']*d['B']/d['ms_median']/1e9, 'TFLOP/s')"; done
+for cfg in "5 2" "6 1" "6 2" "4 3" "5 3"; do set -- $cfg
+  SBP_BSR_VERBOSE=1 SBP_BSR_MT=$1 SBP_BSR_DEPTH=$2 python tools/time_config.py --workload config3 --steps 30 --tag mt$1_d$2 2>&1 | sort -u | cut -c1-170 | grep -v "^k_bsr<"
+done
