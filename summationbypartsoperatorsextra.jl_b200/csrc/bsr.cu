@@ -35,8 +35,14 @@
 //    of the CTA stalled on the store queue at the end of every chunk (2100 of 5150 cycles per chunk, measured with
 //    clock64 stamps) while the tensor pipe idled; beta != 0 or an unaligned dU fall back to that path.
 //  * No CTA-wide barrier after the prologue.
-// Measured (profiles/r1f_*): BASELINE config 3 (N = 1296 cloud, 13.3 nnz/row, B = 65536, fused 2D SAT) 0.344 ms = 247
-// GDOF/s (scalar kernel: 0.80 ms); banded N = 104 apply 0.148 ms = 368 GDOF/s = 90% of the measured HBM peak.
+//  * Per-item constants of a consumer warp come from one 32-byte record per row block, prepared on the host for the
+//    launch's pipeline depth (first fragment, fragment count, rows of the two quads, ring slot of the chunk's window,
+//    flags of the rows that carry a 1D SAT) and fetched one item ahead; alpha = -1 (every RHS call) is folded into the
+//    fragment loads as a sign-bit XOR.
+//  * Odd N: tensor rows are instance PAIRS and the image is that of diag(D, D) (api.cu build_bsr): same data path.
+// Measured (profiles/r1h_*): BASELINE config 3 (N = 1296 cloud, 13.3 nnz/row, B = 65536, fused 2D SAT) 0.325 ms = 262
+// GDOF/s (scalar kernel: 0.80 ms); banded N = 104 apply 0.139 ms = 391 GDOF/s = 96% of the measured HBM peak; config 1
+// batched (N = 101, fused 1D SATs) 0.168 ms = 315 GDOF/s.
 #include <algorithm>
 #include <cuda.h>
 #include "common.cuh"

@@ -185,7 +185,11 @@ class DerivativeOperator:
             return True
         N = D.shape[0]
         if N <= _lib_small_n():
-            return False  # smem-resident DMMA path skips nothing but is already HBM/FP64-rate bound
+            # smem-resident DMMA path: HBM/FP64-rate bound for full matrices.  Banded operators (FD-SBP, the banded RBF
+            # FSBP operators of examples/RBF_FSBP_advection.jl) from N ~ 48 are faster on the block-sparse kernel
+            # (measured, B = 2^19: N = 40: 341 dense vs 293 sparse GDOF/s; 65: 179 vs 314; 101: 168 vs 294; 104: 321 vs
+            # 391; 128: 328 vs 337)
+            return N >= 48 and np.count_nonzero(D) < 0.25 * N * N
         return np.count_nonzero(D) < 0.15 * N * N
 
     def device_op(self, ctx: Context) -> _DeviceOp:

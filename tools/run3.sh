@@ -1,3 +1,8 @@
-for cfg in "5 2" "6 1" "6 2" "4 3" "5 3"; do set -- $cfg
-  SBP_BSR_VERBOSE=1 SBP_BSR_MT=$1 SBP_BSR_DEPTH=$2 python tools/time_config.py --workload config3 --steps 30 --tag mt$1_d$2 2>&1 | sort -u | cut -c1-170 | grep -v "^k_bsr<"
-done
+for n in 32 40 64 65 101 104 128; do for d in "" 1; do
+  SBP_BENCH_DENSE=$d python tools/time_config.py --workload banded --n $n --steps 30 --tag "n${n}_dense${d}" 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:160]); continue
+    print(d['tag'], d['kernel'], round(d['ms_median'],4), 'ms', round(d['gdof_s'],1), 'GDOF/s')"
+done; done
