@@ -317,6 +317,58 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
     return out
 
 
+def config5_sharded(torch, S, ctx, dist, rank, world, dev, steps=3):
+    """BASELINE config 5 at its full size, strong scaling: dense MFSBP-type operator N = 4096 (replicated), batch 65536
+    sharded contiguously over the ranks, mul! + global discrete energy u'Pu (one NCCL allreduce of a scalar per step,
+    inside the timed region).  Device time, max over ranks."""
+    from sbp_b200.sharding import shard_range
+
+    N, Btot = 4096, 65536
+    lo, hi = shard_range(Btot, world, rank)
+    B = hi - lo
+    rng = np.random.default_rng(0)  # same operator on every rank
+    Sk = rng.normal(size=(N, N))
+    Sk = Sk - Sk.T
+    w = rng.uniform(0.5, 1.5, N)
+    w *= 4.0 / w.sum()
+    op = S.upload_dense(ctx, Sk / w[:, None], w)
+    del Sk
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    U = torch.rand((B, N), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    Y = torch.empty_like(U)
+    E = torch.zeros(2, dtype=torch.float64, device=dev)
+    lib, h = ctx._lib, ctx.handle
+
+    def step():
+        S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
+        S._lib.check(lib.sbp_integrate(h, op.handle, C.c_void_p(Y.data_ptr()), None, B, 1, None, C.c_void_p(E.data_ptr())))
+        if dist is not None:
+            dist.all_reduce(E)
+
+    for _ in range(2):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    t1.synchronize()
+    t = torch.tensor([t0.elapsed_time(t1) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    energy = float(E[0].item())
+    del U, Y
+    return {"workload": "config5: dense N=4096 operator x 65536 instances (strong scaling), mul! + global energy allreduce",
+            "ms": ms, "gdof_s": N * Btot / ms / 1e6, "tflops": 2.0 * N * N * Btot / ms / 1e9,
+            "tflops_per_gpu": 2.0 * N * N * Btot / ms / 1e9 / world, "batch_per_gpu": B, "global_energy": energy,
+            "kernel": "k_dense_gemm_tma (TMA + DMMA.8x8x4)", "collective": "ncclAllReduce of 1 double per step" if world > 1 else "none"}
+
+
 def run_native(args):
     import torch
 
@@ -405,6 +457,11 @@ def run_native(args):
     checksum = float(hY[:: max(1, B // 1024)].sum())
     ctx.free_pinned(hU), ctx.free_pinned(hY)
 
+    try:
+        c5 = config5_sharded(torch, S, ctx, dist, rank, world, dev) if not args.no_extra else None
+    except Exception as e:  # pragma: no cover
+        c5 = {"error": str(e)[:200]}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -453,6 +510,8 @@ def run_native(args):
         "clocks": clocks,
         "global_energy_allreduce": global_energy,
     }
+    if c5 is not None:
+        line["config5_sharded"] = c5
     if fp64_dmma:
         line["roofline"]["fp64_frac"] = (line["roofline"]["fp64_tflops_dense_equivalent"] *
                                          line["roofline"]["fp64_flops_executed_fraction"] / fp64_dmma)
@@ -482,7 +541,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 3/4/5)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (configs 1/3/4/5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -488,7 +488,7 @@ def test_subcell_single_operator_known_answers(ctx, coupling):
 
 
 # ---- K5 reductions -------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N", [5, 16, 64, 101, 1296])
+@pytest.mark.parametrize("N", [5, 16, 64, 101, 1296, 4096])
 def test_integrate_modes(ctx, N):
     w = np.random.default_rng(N).uniform(0.1, 1.0, N)
     D = S.MatrixDerivativeOperator(0.0, 1.0, np.linspace(0, 1, N), w, np.zeros((N, N)) + np.eye(N), storage="dense")
