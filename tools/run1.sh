@@ -1,3 +1,2 @@
 P=$PWD/summationbypartsoperatorsextra.jl_b200
-python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-for wl in config3 config1b "banded --n 104" "banded --n 101" "config1b --n 104"; do SBP_BSR_VERBOSE=1 python tools/time_config.py --workload $wl --steps 30 --tag new 2>&1 | sort -u; done 2>&1 | cut -c1-220
+for v in solo1a tracea; do echo == $v; SBP_B200_LIB=$P/libsbp_b200_$v.so python tools/time_config.py --workload config3 --steps 1 2>&1 | grep "warp [0-7] \|ms_median" | sort | uniq | awk "NR%8==1" | cut -c1-200 | head -4; done
