@@ -23,6 +23,7 @@ from .operators import (DerivativeOperator, GaussLegendre, GaussRadauLeft, Gauss
 from .conservation_laws import (AnalysisCallback, MultidimensionalLinearAdvectionNonperiodicSemidiscretization,
                                 ODEProblem, VariableLinearAdvectionNonperiodicSemidiscretization,
                                 analyze_quantities, quantities, semidiscretize, solve_ssprk53, tstops)
+from .container import load_operator, save_operator
 from .sharding import shard_range
 
 __version__ = "0.1.0"

@@ -214,4 +214,43 @@ function analyze_quantities(semi::MultidimensionalLinearAdvectionNonperiodicSemi
     return Array(q)   # 7 x B, rows in the reference's order
 end
 
+# ---- portable operator container (replaces the `.jls` files of examples/RBF_MFSBP.jl:51-52) ---------------------------
+# Flat little-endian binary file, layout documented in ../container.py (`SBPOP001`); read by `sbp_b200.load_operator`.
+#   D = multidimensional_function_space_operator(...)        # built once on the CPU (Optim), as in the reference
+#   SBPB200.export_operator("D_rectangle.sbpop", D)
+function export_operator(path::AbstractString, D::MultidimensionalMatrixDerivativeOperator{Dim, Float64}) where {Dim}
+    N = length(D.weights)
+    Nb = length(D.boundary_indices)
+    open(path, "w") do io
+        write(io, codeunits("SBPOP001"))
+        write(io, Int64[2, N, Dim, Nb, D.accuracy_order, 0])
+        write(io, Float64[0.0, 0.0])
+        for x in grid(D), d in 1:Dim            # nodes, node-major
+            write(io, Float64(x[d]))
+        end
+        write(io, Vector{Float64}(D.weights))
+        write(io, Vector{Int64}(D.boundary_indices))       # 1-based
+        for n in D.normals, d in 1:Dim          # normals, entry-major
+            write(io, Float64(n[d]))
+        end
+        write(io, Vector{Float64}(D.weights_boundary))
+        for d in 1:Dim
+            write(io, Matrix{Float64}(D[d]))    # column-major, as in memory
+        end
+    end
+    return path
+end
+function export_operator(path::AbstractString, D::MatrixDerivativeOperator{Float64})
+    N = length(grid(D))
+    open(path, "w") do io
+        write(io, codeunits("SBPOP001"))
+        write(io, Int64[1, N, 1, 0, D.accuracy_order, 0])
+        write(io, Float64[first(grid(D)), last(grid(D))])
+        write(io, Vector{Float64}(grid(D)))
+        write(io, Vector{Float64}(mass_matrix(D).diag))
+        write(io, Matrix{Float64}(D))
+    end
+    return path
+end
+
 end # module

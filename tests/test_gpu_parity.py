@@ -610,6 +610,23 @@ def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B):
             assert rel_err(out[b], semio.rhs(U[b], 0.0)) <= TOL
 
 
+# ---- operator container -> device -------------------------------------------------------------------
+def test_container_operator_on_device(ctx, tmp_path):
+    D = _scattered_mfsbp(9, seed=4)
+    S.save_operator(tmp_path / "D.sbpop", D)
+    L = S.load_operator(tmp_path / "D.sbpop")
+    a = (1.0, 0.4)
+    g = lambda x, t: np.sin(x[0] + 2 * x[1] - t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(L, a, g, storage="sparse")
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    U = rand_batch(40, D.N, 3)
+    u, du = ctx.upload(U), S.DeviceBatch.empty(ctx, 40, D.N)
+    semi(du, u, None, 0.25)
+    assert rel_err(du.to_host(), np.stack([semio.rhs(v, 0.25) for v in U])) <= TOL
+    for dim in (0, 1):
+        assert rel_err((L[dim] * u).to_host(), O.apply_batch(D.Ds[dim], U)) <= TOL
+
+
 # ---- committed golden fixtures (tests/golden/hotpath_golden.npz, generated by tests/golden/make_golden.py) ---------
 def test_golden_fixtures(ctx):
     import os
