@@ -196,6 +196,10 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
  * Runge-Kutta schemes the examples use (SSPRK53, RDPK3SpFSAL49) so that a step never leaves the device. */
 int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a,
                      double b, double c);
+/* Y = a*X + b*Y + c*Z + d*W in one pass (Z, W may be NULL; Y is not read when b == 0): a whole stage update
+ * u3 = a30*u + a32*u2 + b32*h*f(u2) of SSPRK53 (examples/RBF_FSBP_advection.jl:45-51) reads three vectors once. */
+int32_t sbp_lincomb(sbp_ctx* ctx, double* Y, const double* X, const double* Z, const double* W, int64_t n, double a,
+                    double b, double c, double d);
 
 /* ---- multi-GPU: one process per GPU; the only collective is a sum of a few scalars ------------- */
 #define SBP_NCCL_ID_BYTES 128

@@ -90,6 +90,7 @@ SIGNATURES = {
     "sbp_rhs_advection2d": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "sbp_rhs_advection1d": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "sbp_axpbypcz": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, c_dbl]),
+    "sbp_lincomb": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, c_dbl, c_dbl]),
     "sbp_comm_unique_id": (c_i32, [c_void_p]),
     "sbp_comm_init": (c_i32, [c_void_p, c_i32, c_i32, c_void_p]),
     "sbp_allreduce_sum": (c_i32, [c_void_p, c_void_p, c_i32]),

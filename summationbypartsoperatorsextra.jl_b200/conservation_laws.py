@@ -255,7 +255,7 @@ _SSPRK53 = dict(
 
 def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None = None) -> DeviceBatch:
     """Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive=false)`, examples/RBF_FSBP_advection.jl:45-51) with
-    every stage update on the device (sbp_axpbypcz); returns the final state."""
+    every stage update one pass on the device (sbp_lincomb); returns the final state."""
     k = _SSPRK53
     u: DeviceBatch = prob.u0
     semi, p = prob.f, prob.p
@@ -268,15 +268,15 @@ def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None
     while t < tend - 1e-14:
         h = min(dt, tend - t)
         semi(du, u, p, t)
-        u1.axpby_(1.0, u, 0.0).axpby_(k["b10"] * h, du)                       # u1 = u + b10 h f(u)
+        u1.lincomb_(1.0, u, k["b10"] * h, du)                                 # u1 = u + b10 h f(u)
         semi(du, u1, p, t + k["c1"] * h)
-        u2.axpby_(1.0, u1, 0.0).axpby_(k["b21"] * h, du)                      # u2 = u1 + b21 h f(u1)
+        u2.lincomb_(1.0, u1, k["b21"] * h, du)                                # u2 = u1 + b21 h f(u1)
         semi(du, u2, p, t + k["c2"] * h)
-        u3.axpby_(k["a30"], u, 0.0, k["a32"], u2).axpby_(k["b32"] * h, du)    # u3 = a30 u + a32 u2 + b32 h f(u2)
+        u3.lincomb_(k["a30"], u, k["a32"], u2, k["b32"] * h, du)              # u3 = a30 u + a32 u2 + b32 h f(u2)
         semi(du, u3, p, t + k["c3"] * h)
-        u1.axpby_(k["a40"], u, 0.0, k["a43"], u3).axpby_(k["b43"] * h, du)    # u4 (in u1)
+        u1.lincomb_(k["a40"], u, k["a43"], u3, k["b43"] * h, du)              # u4 (in u1)
         semi(du, u1, p, t + k["c4"] * h)
-        u.axpby_(k["a52"], u2, 0.0, k["a54"], u1).axpby_(k["b54"] * h, du)    # u5
+        u.lincomb_(k["a52"], u2, k["a54"], u1, k["b54"] * h, du)              # u5
         t += h
         step += 1
         if callback is not None and callback.should_fire(step, t, t >= tend - 1e-14):

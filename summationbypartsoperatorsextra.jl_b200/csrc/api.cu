@@ -1120,6 +1120,16 @@ int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, 
     return launch_axpbypcz(ctx, Y, X, Z, n, a, b, c);
 }
 
+int32_t sbp_lincomb(sbp_ctx* ctx, double* Y, const double* X, const double* Z, const double* W, int64_t n, double a,
+                    double b, double c, double d) {
+    SBP_REQUIRE(ctx, SBP_EINVAL, "null ctx");
+    SBP_REQUIRE(n >= 0, SBP_EDIM, "negative length");
+    if (n == 0) return SBP_OK;
+    SBP_REQUIRE(Y && X, SBP_EINVAL, "null vector");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    return launch_lincomb(ctx, Y, X, Z, W, n, a, b, c, d);
+}
+
 // ---- multi-GPU --------------------------------------------------------------------------------------
 int32_t sbp_comm_unique_id(char id[SBP_NCCL_ID_BYTES]) {
     SBP_REQUIRE(id, SBP_EINVAL, "null id");

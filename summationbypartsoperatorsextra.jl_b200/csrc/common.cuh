@@ -180,6 +180,8 @@ int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const do
 int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t B, double factor, int inverse);
 int32_t launch_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,
                         double c);
+int32_t launch_lincomb(sbp_ctx* ctx, double* Y, const double* X, const double* Z, const double* W, int64_t n, double a,
+                       double b, double c, double d);
 int32_t launch_sum_partials(sbp_ctx* ctx, const double* partials, int n, double* out);
 int32_t launch_adv2d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B,
                               const double* g, int64_t g_stride, double* quantities, bool apply_sat);

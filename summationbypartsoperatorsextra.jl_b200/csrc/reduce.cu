@@ -148,58 +148,60 @@ int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t 
     return SBP_OK;
 }
 
-// ---- Y = a X + b Y + c Z --------------------------------------------------------------------------
-template <bool HASZ>
-__global__ void __launch_bounds__(256) k_axpbypcz(double* __restrict__ Y, const double* __restrict__ X,
-                                                  const double* __restrict__ Z, long long n, double a, double b,
-                                                  double c) {
+// ---- Y = a X + b Y + c Z + d W ------------------------------------------------------------------------
+// Stage updates of the explicit Runge-Kutta schemes in ONE pass (SSPRK53's u3 = a30 u + a32 u2 + b32 h f(u2) reads three
+// vectors and writes one).  Y is read only when b != 0 (it may be uninitialised memory otherwise); Z, W may be NULL.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_lincomb(double* __restrict__ Y, const double* __restrict__ X,
+                                                 const double* __restrict__ Z, const double* __restrict__ W,
+                                                 long long n, double a, double b, double c, double d) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long n2 = n / 2;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
-        const double2 x = reinterpret_cast<const double2*>(X)[i];
-        double2 y = reinterpret_cast<double2*>(Y)[i];
-        // b == 0 must not read Y (it may hold NaN/Inf from uninitialised memory)
-        y.x = (b == 0.0) ? a * x.x : fma(a, x.x, b * y.x);
-        y.y = (b == 0.0) ? a * x.y : fma(a, x.y, b * y.y);
-        if (HASZ) {
-            const double2 z = reinterpret_cast<const double2*>(Z)[i];
-            y.x = fma(c, z.x, y.x);
-            y.y = fma(c, z.y, y.y);
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        const long long n2 = n / 2;
+        for (long long i = i0; i < n2; i += stride) {
+            const double2 x = ldg_stream2(X + 2 * i);
+            double2 y = make_double2(a * x.x, a * x.y);
+            if (b != 0.0) {
+                const double2 o = reinterpret_cast<const double2*>(Y)[i];
+                y.x = fma(b, o.x, y.x), y.y = fma(b, o.y, y.y);
+            }
+            if (Z) {
+                const double2 z = ldg_stream2(Z + 2 * i);
+                y.x = fma(c, z.x, y.x), y.y = fma(c, z.y, y.y);
+            }
+            if (W) {
+                const double2 w = ldg_stream2(W + 2 * i);
+                y.x = fma(d, w.x, y.x), y.y = fma(d, w.y, y.y);
+            }
+            reinterpret_cast<double2*>(Y)[i] = y;
         }
-        reinterpret_cast<double2*>(Y)[i] = y;
     }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        double y = (b == 0.0) ? a * X[n - 1] : fma(a, X[n - 1], b * Y[n - 1]);
-        if (HASZ) y = fma(c, Z[n - 1], y);
-        Y[n - 1] = y;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_axpbypcz_scalar(double* __restrict__ Y, const double* __restrict__ X,
-                                                         const double* __restrict__ Z, long long n, double a,
-                                                         double b, double c) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        double y = (b == 0.0) ? a * X[i] : fma(a, X[i], b * Y[i]);
+    for (long long i = (VEC ? 2 * (n / 2) : 0) + i0; i < n; i += stride) {
+        double y = a * X[i];
+        if (b != 0.0) y = fma(b, Y[i], y);
         if (Z) y = fma(c, Z[i], y);
+        if (W) y = fma(d, W[i], y);
         Y[i] = y;
     }
 }
 
-int32_t launch_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,
-                        double c) {
+int32_t launch_lincomb(sbp_ctx* ctx, double* Y, const double* X, const double* Z, const double* W, int64_t n, double a,
+                       double b, double c, double d) {
     int grid = (int)std::max<long long>(1, std::min<long long>((n / 2 + 255) / 256, (long long)ctx->sm_count * 16));
     const bool aligned = ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(X) |
-                           reinterpret_cast<uintptr_t>(Z)) & 15) == 0;
-    if (!aligned)
-        k_axpbypcz_scalar<<<grid, 256, 0, ctx->stream>>>(Y, X, Z, n, a, b, c);
-    else if (Z)
-        k_axpbypcz<true><<<grid, 256, 0, ctx->stream>>>(Y, X, Z, n, a, b, c);
+                           reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+    if (aligned)
+        k_lincomb<true><<<grid, 256, 0, ctx->stream>>>(Y, X, Z, W, n, a, b, c, d);
     else
-        k_axpbypcz<false><<<grid, 256, 0, ctx->stream>>>(Y, X, Z, n, a, b, c);
+        k_lincomb<false><<<grid, 256, 0, ctx->stream>>>(Y, X, Z, W, n, a, b, c, d);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
+}
+int32_t launch_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,
+                        double c) {
+    return launch_lincomb(ctx, Y, X, Z, nullptr, n, a, b, c, 0.0);
 }
 
 // ---- 2D advection: SAT epilogue (when A was applied by a dense kernel) + analysis quantities ----------

@@ -238,6 +238,18 @@ class DeviceBatch:
                                          float(b), float(c)))
         return self
 
+    def lincomb_(self, a: float, x: "DeviceBatch", c: float = 0.0, z: "DeviceBatch | None" = None, d: float = 0.0,
+                 w: "DeviceBatch | None" = None, b: float = 0.0):
+        """self <- a*x + c*z + d*w (+ b*self) in one pass over memory (`sbp_lincomb`)."""
+        for v in (x, z, w):
+            if v is not None and v.shape != self.shape:
+                raise DimensionMismatch("lincomb_: shapes differ")
+        check(self.ctx._lib.sbp_lincomb(self.ctx.handle, C.c_void_p(self.ptr), C.c_void_p(x.ptr),
+                                        C.c_void_p(z.ptr) if z is not None else None,
+                                        C.c_void_p(w.ptr) if w is not None else None, self.B * self.N, float(a),
+                                        float(b), float(c), float(d)))
+        return self
+
     def free(self):
         if isinstance(self._owner, RawBuffer):
             self._owner.free()

@@ -627,6 +627,21 @@ def test_container_operator_on_device(ctx, tmp_path):
         assert rel_err((L[dim] * u).to_host(), O.apply_batch(D.Ds[dim], U)) <= TOL
 
 
+def test_lincomb_stage_update(ctx):
+    """sbp_lincomb: Y = a X + b Y + c Z + d W in one pass (RK stage updates); Y is not read when b == 0."""
+    for n_inst, N in ((1, 1), (3, 7), (257, 64), (1000, 101)):
+        X, Z, W, Y0 = (rand_batch(n_inst, N, s) for s in (1, 2, 3, 4))
+        x, z, w = ctx.upload(X), ctx.upload(Z), ctx.upload(W)
+        y = ctx.upload(np.full_like(Y0, np.nan))
+        y.lincomb_(0.3, x, -1.25, z, 2.0, w)
+        assert np.allclose(y.to_host(), 0.3 * X - 1.25 * Z + 2.0 * W, rtol=1e-15, atol=1e-15)
+        y = ctx.upload(Y0)
+        y.lincomb_(0.3, x, 0.5, z, b=-2.0)
+        assert np.allclose(y.to_host(), 0.3 * X + 0.5 * Z - 2.0 * Y0, rtol=1e-15, atol=1e-15)
+        y.lincomb_(1.0, x)
+        assert np.array_equal(y.to_host(), X)
+
+
 # ---- committed golden fixtures (tests/golden/hotpath_golden.npz, generated by tests/golden/make_golden.py) ---------
 def test_golden_fixtures(ctx):
     import os
