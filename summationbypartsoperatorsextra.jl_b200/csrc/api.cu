@@ -476,11 +476,19 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
         m = std::min(m, cmin[c]);
         blo[c] = m / BX;
     }
-    for (int rb = 0; rb < nrb; rb++)
+    // pos3: the same codes as byte offsets into the ring for every tile size MT = 1..8 (box = 8 MT instances x BX nodes)
+    std::vector<int> pos3(8 * pos.size(), 0);
+    int maxnf = 0;
+    for (int rb = 0; rb < nrb; rb++) {
+        maxnf = std::max(maxnf, rbf[rb + 1] - rbf[rb]);
         for (int f = rbf[rb] * PS; f < rbf[rb + 1] * PS; f++) {
             const int n = pos[f];
-            pos[f] = ((n / BX - blo[rb / CH]) << 8) | (n % BX);
+            const int brel = n / BX - blo[rb / CH];
+            pos[f] = (brel << 8) | (n % BX);
+            for (int mt = 1; mt <= 8; mt++) pos3[(size_t)(mt - 1) * pos.size() + f] = brel * (8 * mt * BX * 8) + (n % BX) * 8;
         }
+    }
+    op->bsr_maxnf = maxnf;
     // ring sizes: in the virtual box stream (tile k occupies boxes [k*nbt, (k+1)*nbt)) the boxes of item s may only
     // overwrite slots that no item >= s - d still needs
     const int nbt = (N + BX - 1) / BX;
@@ -497,7 +505,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
         rbmeta[4 * rb + 2] = rows[2 * rb];
         rbmeta[4 * rb + 3] = rows[2 * rb + 1];
     }
-    for (int d = 0; d < 4; d++) {
+    for (int d = 0; d < kBsrDepths; d++) {
         long long need = 1;
         const int items = nch * (d + 2);
         for (int s = 0; s < items; s++) {
@@ -511,14 +519,15 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     // per-row-block records read by the consumer warps, one array per pipeline depth d (the ring size differs):
     // {first fragment relative to the chunk, fragments, first row of quad A, of quad B | ring slot of the chunk's lowest
     // box (blo % nbox[d]), blo, 0, 0}; padded to whole chunks with inactive records (rows >= N, no fragments)
-    std::vector<int> item(4 * (size_t)nch * CH * 8, 0);
-    for (int d = 0; d < 4; d++)
+    std::vector<int> item((size_t)kBsrDepths * nch * CH * 8, 0);
+    for (int d = 0; d < kBsrDepths; d++)
         for (int rb = 0; rb < nch * CH; rb++) {
             int* e = &item[((size_t)d * nch * CH + rb) * 8];
             if (rb < nrb) {
                 for (int k = 0; k < 4; k++) e[k] = rbmeta[4 * rb + k];
                 e[4] = blo[rb / CH] % op->bsr_nbox[d];
                 e[5] = blo[rb / CH];
+                e[7] = rbf[rb];  // absolute first fragment (bsr3.cu reads the fragments straight from the image)
                 // rows of the block that carry a 1D SAT: bit k = block row k is node 0 of its instance, bit 8 + k = node N1 - 1
                 for (int k = 0; k < 8; k++) {
                     const int r = block_row(rb, k);
@@ -541,6 +550,8 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     }
     int32_t rc = upload(&op->d_bsr_val, frag);
     if (!rc) rc = upload(&op->d_bsr_pos, pos);
+    if (pos3.empty()) pos3.assign(8 * PS, 0);
+    if (!rc) rc = upload(&op->d_bsr_pos3, pos3);
     if (!rc) rc = upload(&op->d_bsr_rbmeta, rbmeta);
     if (!rc) rc = upload(&op->d_bsr_chmeta, chmeta);
     if (!rc) rc = upload(&op->d_bsr_item, item);
@@ -736,7 +747,7 @@ int32_t sbp_op_destroy(sbp_op* op) {
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
                     op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
-                    op->d_rb_bdiag,  op->d_bsr_item};
+                    op->d_rb_bdiag,  op->d_bsr_item, op->d_bsr_pos3};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;

@@ -47,6 +47,7 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "bsr.cuh"
 
 // -DSBP_BSR_TRACE: per-warp cycle accounting of the consumer phases (clock64 stamps; block 0 prints its totals)
 #ifdef SBP_BSR_TRACE
@@ -63,43 +64,6 @@ namespace sbp {
 constexpr int kBsrMaxStages = 4;
 // consumer warps = kBsrGroups * kBsrCH * MH: warp = (group, row block of the chunk, m-half); a warp owns MTW m-tiles
 // (8 instances each) of the tile's TI = 8 * MTW * MH instances; + 2 producer warps
-
-struct BsrParams {
-    const double* __restrict__ U;
-    double* __restrict__ dU;
-    const double* __restrict__ val;   // [fragment][32]
-    const int* __restrict__ pos;      // [fragment][4]  (box - boxlo[chunk]) << 8 | node % kBsrBX
-    const int4* __restrict__ item;    // [nch * kBsrCH][2] consumer records for this launch's pipeline depth (api.cu build_bsr)
-    const int4* __restrict__ rbmeta;  // [nrb] {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
-    const int4* __restrict__ chmeta;  // [nch] {first fragment, end fragment, boxlo, boxhi}: boxes [0, boxhi) of the tile are
-                                      // resident once the chunk has been staged; no later chunk touches a box below boxlo
-    int N, nrb, nch, nbox, nbt, maxf, nst;  // nbox ring slots, nbt boxes per tile, nst pipeline stages
-    int Nh;                           // nodes per instance: N, or N/2 when a tensor row holds an instance PAIR (odd Nh)
-    long long B;                      // tensor rows (instances, or instance pairs)
-    double alpha, beta;
-    // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
-    const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows
-    const double* __restrict__ g;
-    long long g_stride;
-    Sat1D sat;                        // fused 1D SATs (rows 0 and N-1)
-};
-
-// TMA 2-D tensor copy: box {kBsrBX nodes, TI instances} at (node x, instance y) -> shared memory, completion on mbarrier
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int x, int y, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::
-            "r"(smem_u32(smem_dst)),
-        "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// TMA 2-D tensor store: box {4 rows, instances} from shared memory -> dU (bulk async-group completion); rows beyond N
-// and instances beyond B are clipped by the hardware
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, int x, int y, const void* smem_src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n" ::"l"(tmap), "r"(x),
-                 "r"(y), "r"(smem_u32(smem_src))
-                 : "memory");
-}
 
 // OUT: how results leave the SM.  0: 8-byte stores (dU not 16-byte aligned), 1: 16-byte stores, 2: staged in shared
 // memory and written by TMA tensor stores (beta == 0): asynchronous, so the output stream overlaps the next chunk's
@@ -642,6 +606,10 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         B /= 2;  // tensor rows = instance pairs
     }
     p.B = B;
+    {
+        int32_t rc3 = SBP_OK;
+        if (launch_bsr3(ctx, op, p, satmode, vec, &rc3)) return rc3;  // lean consumer loop (bsr3.cu) when it applies
+    }
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller
     // tiles so that every SM gets work.  SBP_BSR_MT / SBP_BSR_DEPTH override (tuning).

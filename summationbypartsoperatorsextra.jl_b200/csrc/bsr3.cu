@@ -1,0 +1,533 @@
+// bsr3.cu -- K2'/K3', experimental second generation of the block-sparse DMMA kernel (bsr.cu); OPT-IN (SBP_BSR_V3=1|2).
+// Same operator image, data movement (TMA box ring, operator fragments per chunk by bulk copy, TMA tensor stores) and
+// barrier protocol as k_bsr, with a leaner consumer loop and the tooling used to find out what bounds the kernel.
+//
+// Reference math as in bsr.cu: y = alpha*scale*D u + beta*y and du = -A u + B (u - tmp1)
+// (src/conservation_laws/multidimensional_linear_advection.jl:60-81), 1D SATs of the upstream semidiscretization.
+//
+// Differences to k_bsr:
+//  * ring addresses of the A-operand gathers come precomputed from the host as BYTE offsets for the launch's tile size
+//    (sbp_op::d_bsr_pos3): per fragment one add, one unsigned min (wrap) and one add instead of shift/mask/compare/
+//    select/multiply-add; the chain is unrolled by two fragments over two explicit A-operand register sets, operands are
+//    fetched by ld.shared at 32-bit addresses with compile-time m-tile offsets, one fragment ahead;
+//  * loop invariants that the compiler rematerialised at every use are pinned in registers, the warp index is made
+//    provably uniform (TMA stores without the per-lane vote loops), item records are fetched two items ahead;
+//  * box stages and operator-fragment stages are decoupled (p.nst box stages, two fragment stages): with plain 16-byte
+//    stores (no staging buffers) the ring of config 3 holds two chunks of lookahead at 56 instances per tile;
+//  * -DSBP_B3_EXP=n what-if builds and SBP_BSR_SKEW (start-up delay of every second consumer warp).
+// Result (profiles/r1k_bsr3_notes.txt): 14 % fewer warp instructions, 15 % less time outside the DMMA chain -- and the
+// same 0.326-0.330 ms on BASELINE config 3 as k_bsr (banded 1D operators: slower).  The what-if builds show why: without
+// DMMAs 0.252 ms, without output 0.166 ms (= the tensor pipe: 2 warps x 64 DMMA x 16 cycles per scheduler and chunk),
+// full kernel 0.330 ms = pipe time + the non-chain time of a warp: the two consumer warps of a scheduler run their
+// chains at the same time and their scalar phases at the same time, whatever the pipeline depth, the start-up skew or
+// the length of the scalar phase (time saved there reappears as waiting on the stage barrier).  An intermediate version
+// that fetched the operator fragments from the L2-resident image straight into registers (no fragment stages at all)
+// was 30 % SLOWER: the L2 round trip under load is exposed once per item.
+#include <algorithm>
+#include "bsr.cuh"
+
+// -DSBP_B3_EXP=n: what-if builds for bottleneck hunting (WRONG RESULTS): 1 = no DMMA, 2 = no A-operand loads inside the chain,
+// 3 = no TMA box loads, 4 = no output
+#ifndef SBP_B3_EXP
+#define SBP_B3_EXP 0
+#endif
+
+namespace sbp {
+
+#if SBP_B3_EXP == 1
+#define B3_DMMA(c0, c1, a, b) asm volatile("" ::"d"(a), "d"(b))
+#else
+#define B3_DMMA(c0, c1, a, b) dmma884(c0, c1, a, b)
+#endif
+
+constexpr int kB3Stages = 4;      // box stages (mbarrier pairs)
+constexpr int kB3FragStages = 2;  // operator-fragment stages
+
+// shared-memory loads at a 32-bit shared address + compile-time offset (volatile: they keep their place in the software pipeline)
+template <uint32_t OFF>
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];\n" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <uint32_t OFF>
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];\n" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int MT, uint32_t MTB, int I = 0>
+__device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
+    if constexpr (I < MT) {
+        a[I] = lds64<I * MTB>(addr);
+        lds_tiles<MT, MTB, I + 1>(a, addr);
+    }
+}
+
+template <int MT, int SAT, int OUT>
+__global__ void __launch_bounds__((kBsrCH + 2) * 32)
+    k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
+    constexpr bool VEC = OUT == 1 || OUT == 2;
+    constexpr int BX = kBsrBX;
+    constexpr int TI = 8 * MT;
+    constexpr int CONS = kBsrCH;               // consumer warps: one row block of the chunk each
+    constexpr int BOX = TI * BX;               // doubles per box
+    constexpr uint32_t BOXB = BOX * 8;         // bytes per box
+    constexpr uint32_t MTB = 8 * BX * 8;       // byte distance between the m-tiles of a lane
+    constexpr int PS = 4;                      // ring codes per fragment
+    extern __shared__ __align__(128) double smem[];
+    // boxes and operator fragments have separate stage counts: p.nst box stages (HBM latency: as deep as the ring allows),
+    // kB3FragStages fragment stages (L2 latency: two are enough, each costs maxf * 272 bytes)
+    __shared__ uint64_t bar_full[kB3Stages], bar_empty[kB3Stages], fbar_full[kB3FragStages], fbar_empty[kB3FragStages];
+    double* s_u = smem;                                                              // nbox * BOX
+    double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
+    int* s_pos = reinterpret_cast<int*>(s_val + (size_t)kB3FragStages * p.maxf * 32);  // kB3FragStages * maxf * PS
+    // output staging, per consumer warp: [quad A | quad B][8 * MT instances][4 rows]  (128-byte aligned)
+    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)kB3FragStages * p.maxf * PS + 31) & ~(size_t)31));
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
+    const int N = p.N, nst = p.nst, nbox = p.nbox;
+    const long long ntiles = (p.B + TI - 1) / TI;
+    const int stepb = p.nbt % nbox;  // ring offset advance per tile (in boxes)
+    const bool alpha_m1 = p.alpha == -1.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nst; s++) {
+            mbar_init(&bar_full[s], 1);      // the box producer's arrive.expect_tx
+            mbar_init(&bar_empty[s], CONS);  // lane 0 of every consumer warp
+        }
+        for (int s = 0; s < kB3FragStages; s++) {
+            mbar_init(&fbar_full[s], 1);
+            mbar_init(&fbar_empty[s], CONS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp >= CONS) {
+        // ------- producers (as in bsr.cu): warp CONS requests the boxes of the batch, warp CONS + 1 the operator fragments -------
+        if (lane == 0) {
+            const bool boxes = warp == CONS;
+            const int pst = boxes ? nst : kB3FragStages;  // stages of this producer's barrier set
+            uint64_t* const pfull = boxes ? bar_full : fbar_full;
+            uint64_t* const pempty = boxes ? bar_empty : fbar_empty;
+            int st = 0, round = 0, slot = 0;
+            const uint32_t s_u32 = smem_u32(s_u), s_val32 = smem_u32(s_val), s_pos32 = smem_u32(s_pos);
+            const uint32_t full32 = smem_u32(pfull);
+            int4 cm = __ldg(p.chmeta);
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b0 = (int)(tile * TI);
+                int jb = 0, x = 0;  // boxes of this tile already requested, node coordinate of the next box
+                for (int c = 0; c < p.nch; c++) {
+                    const int4 cmn = __ldg(p.chmeta + (c + 1 < p.nch ? c + 1 : 0));
+                    if (round > 0) mbar_wait(&pempty[st], (round - 1) & 1);
+                    const uint32_t bar = full32 + 8u * st;
+                    if (boxes) {
+                        const int jn = cm.w;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                                     "r"(SBP_B3_EXP == 3 ? 0u : (unsigned)(jn - jb) * BOXB)
+                                     : "memory");
+                        if (SBP_B3_EXP == 3) jb = jn;
+                        for (; jb < jn; jb++, x += BX) {
+                            const uint32_t dst = s_u32 + (uint32_t)slot * BOXB;
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
+                                "{%2, %3}], [%4];\n" ::"r"(dst),
+                                "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
+                                : "memory");
+                            if (++slot == nbox) slot = 0;
+                        }
+                    } else {
+                        const unsigned nfr = (unsigned)(cm.y - cm.x);
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
+                                     "r"(nfr * (256u + 4u * PS))
+                                     : "memory");
+                        if (nfr) {
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                                    "r"(s_val32 + (uint32_t)st * (uint32_t)(p.maxf * 256)),
+                                "l"(p.val + (size_t)cm.x * 32), "r"(nfr * 256u), "r"(bar)
+                                : "memory");
+                            asm volatile(
+                                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                                    "r"(s_pos32 + (uint32_t)st * (uint32_t)(p.maxf * 4 * PS)),
+                                "l"(p.pos + (size_t)cm.x * PS), "r"(nfr * 4u * PS), "r"(bar)
+                                : "memory");
+                        }
+                    }
+                    if (++st == pst) st = 0, round++;
+                    cm = cmn;
+                }
+                // boxes of the tile that no chunk needs are skipped: keep slot == (virtual box index) mod nbox
+                slot += (p.nbt - jb) % nbox;
+                if (slot >= nbox) slot -= nbox;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------- consumers ----------------------------------------
+    const int g = lane >> 2, t = lane & 3;
+    const int Nh = p.Nh;
+    const bool paired = Nh != N;
+    const uint32_t ringB = (uint32_t)nbox * BOXB;
+    const char* const su_lane = reinterpret_cast<const char*>(s_u + g * BX);  // tensor row 8 mt + g lives MTB * mt further
+    double* const so = s_out + (size_t)warp * (2 * 8 * MT * 4);
+    double* const sq = so + (t >> 1) * (8 * MT * 4) + g * 4 + (t & 1) * 2;
+
+    // item records (one per row block, independent of the tile): fetched two items ahead
+    struct Rec {
+        int4 a;      // {first fragment relative to the chunk, fragments, first row of quad A, of quad B}
+        int4 b;      // {ring slot of the chunk's lowest box, lowest box, 1D SAT flags, -}
+        double2 sb;  // 2D SAT coefficients of the lane's two rows (0: none)
+    };
+    const int4* const items = p.item + 2 * warp;
+    const double2* const sbs = reinterpret_cast<const double2*>(p.rb_bdiag) + 4 * warp + t;
+    auto load_rec = [&](int c) {
+        Rec r;
+        r.a = __ldg(items + c * (2 * kBsrCH));
+        r.b = __ldg(items + c * (2 * kBsrCH) + 1);
+        r.sb = make_double2(0.0, 0.0);
+        if (SAT == 1) r.sb = __ldg(sbs + c * (4 * kBsrCH));
+        return r;
+    };
+
+    int c = 0, st = 0, phase = 0, fst = 0, fphase = 0;
+    int tile = blockIdx.x, b0 = blockIdx.x * TI;  // B < 2^31 (checked by the launcher)
+    uint32_t offB = 0;                            // ring offset of the tile's box 0 (bytes)
+    const uint32_t stepB = (uint32_t)stepb * BOXB;
+    const int ntl = (int)ntiles, tstep = gridDim.x * TI, Bi = (int)p.B;
+    Rec r0 = load_rec(0), r1 = load_rec(1 % p.nch);
+    int c2 = 2 % p.nch;
+    double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0;
+    if (SAT == 2) {
+        sat_iw0 = 1.0 / p.sat.w0, sat_iwN = 1.0 / p.sat.wN;
+        if (p.sat.bc_stride == 0) sat_lb = __ldg(p.sat.bc), sat_rb = __ldg(p.sat.bc + 1);
+    }
+    // loop invariants the compiler would otherwise rematerialise at every use: pinned in registers
+    int sgn = alpha_m1 ? (int)0x80000000u : 0;
+    uint32_t su32 = smem_u32(su_lane), ringBr = ringB;
+    uint32_t sval32 = smem_u32(s_val) + lane * 8, spos32 = smem_u32(s_pos) + t * 4;  // stage 0, this lane
+    uint32_t stvalB = (uint32_t)p.maxf * 256u, stposB = (uint32_t)p.maxf * (4u * PS);
+    asm volatile("" : "+r"(sgn), "+r"(su32), "+r"(ringBr), "+r"(sval32), "+r"(spos32), "+r"(stvalB), "+r"(stposB));
+    // (routed through a shuffle: ptxas does not rematerialise a shuffle result from the constant bank)
+    auto pin = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
+    const int nch = pin(p.nch), Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
+    const int scale_needed = pin(alpha_m1 ? 0 : 1);
+    const uint32_t stepBr = (uint32_t)pin((int)stepB);
+    sgn = pin(sgn);
+    uint32_t svst = sval32, spst = spos32;  // fragment buffers of stage st
+
+    if (p.skew > 0 && warp >= 4) {  // de-phase the two consumer warps of a scheduler (chains against scalar phases)
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.skew) {
+        }
+    }
+    while (tile < ntlr) {
+        const Rec r2 = load_rec(c2);  // record of the item after the next one
+        if (++c2 == nch) c2 = 0;
+        const int nf = r0.a.y;
+        const bool active = r0.a.z < Nr;  // padding records of the last chunk carry rows >= N and no fragments
+        // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
+        uint32_t baseB = (uint32_t)r0.b.x * BOXB + offB;
+        baseB = min(baseB, baseB - ringBr);
+        asm volatile("" : "+r"(baseB));
+        const double2 sb = r0.sb;
+        const int r0w = (t < 2 ? r0.a.z : r0.a.w - 4) + 2 * t;  // lane owns rows r0w, r0w + 1 (pair t of the block)
+        // b_j != 0 tested on the bit pattern (no trip through the FP64 pipe)
+        const int mask = (SAT == 1) ? ((((__double2hiint(sb.x) << 1) | __double2loint(sb.x)) != 0 ? 1 : 0) |
+                                       (((__double2hiint(sb.y) << 1) | __double2loint(sb.y)) != 0 ? 2 : 0))
+                                    : 0;
+        const int h0 = (paired && r0w >= Nh) ? 1 : 0, h1 = (paired && r0w + 1 >= Nh) ? 1 : 0;
+        const int n0 = r0w - h0 * Nh, n1 = r0w + 1 - h1 * Nh;
+        double gs0 = 0.0, gs1 = 0.0;
+        if (SAT == 1 && mask && p.g_stride == 0) {
+            if (mask & 1) gs0 = __ldg(p.g + n0);
+            if (mask & 2) gs1 = __ldg(p.g + n1);
+        }
+        double acc[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
+        // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
+        uint32_t sv = svst + (uint32_t)r0.a.x * 256u, sp = spst + (uint32_t)r0.a.x * (4u * PS);
+        const uint32_t spl = sp + (uint32_t)(nf - 1) * (4u * PS);  // last code of the block (look-ahead loads are clamped to it)
+
+        mbar_wait(&fbar_full[fst], fphase);
+        mbar_wait(&bar_full[st], phase);
+        // ---- DMMA chain, two fragments per trip: operands one fragment ahead, ring codes two ahead ----
+        if (active && nf > 0) {
+            // byte code -> shared address of the lane's A operand (m-tile 0): add the window base, wrap, add the lane's row
+            auto conv = [&](uint32_t q) {
+                const uint32_t v = q + baseB;
+                return su32 + min(v, v - ringBr);  // v < 2 ringB: subtracts ringB iff v >= ringB (unsigned wrap otherwise)
+            };
+            auto flip = [&](double v) { return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v)); };
+            double a0[MT], a1[MT];
+            double b0v = flip(lds64<0>(sv));
+            lds_tiles<MT, MTB>(a0, conv(lds32<0>(sp)));
+            uint32_t adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
+            int rem = nf;
+            while (rem >= 2) {
+#if SBP_B3_EXP != 2
+                lds_tiles<MT, MTB>(a1, adr);
+#else
+                a1[0] = __longlong_as_double(adr);
+#endif
+                const double b1v = flip(lds64<256>(sv));
+                adr = conv(lds32<0>(min(sp + 8u * PS, spl)));
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a0[mt], b0v);
+#if SBP_B3_EXP != 2
+                lds_tiles<MT, MTB>(a0, adr);
+#else
+                a0[0] = __longlong_as_double(adr);
+#endif
+                // fragment 2 of this trip = fragment 0 of the next one (unused past the end)
+                b0v = flip(lds64<512>(sv));
+                adr = conv(lds32<0>(min(sp + 12u * PS, spl)));
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a1[mt], b1v);
+                sv += 512u, sp += 8u * PS, rem -= 2;
+            }
+            if (rem) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a0[mt], b0v);
+            }
+        }
+
+        const int nb = min(Bir - b0, TI);
+        if (active) {
+            if (scale_needed) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) acc[mt][0] *= p.alpha, acc[mt][1] *= p.alpha;
+            }
+            // element offset of node r of the lane's tensor row (m-tile 0) inside the ring: r lies in the chunk's window
+            auto ring_elem = [&](int r) {
+                const int q = r / BX;
+                uint32_t o = baseB + (uint32_t)(q - r0.b.y) * BOXB + (uint32_t)(r - q * BX) * 8u;
+                return min(o, o - ringB);
+            };
+            if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
+                const uint32_t o0 = ring_elem(r0w), o1 = ring_elem(r0w + 1);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    if (p.g_stride != 0) {  // per-instance boundary data
+                        const int il = 8 * mt + g;
+                        const long long row = b0 + (il < nb ? il : 0);
+                        if (mask & 1) gs0 = __ldg(p.g + (paired ? 2 * row + h0 : row) * p.g_stride + n0);
+                        if (mask & 2) gs1 = __ldg(p.g + (paired ? 2 * row + h1 : row) * p.g_stride + n1);
+                    }
+                    if (mask & 1) acc[mt][0] += sb.x * (*reinterpret_cast<const double*>(su_lane + o0 + mt * MTB) - gs0);
+                    if (mask & 2) acc[mt][1] += sb.y * (*reinterpret_cast<const double*>(su_lane + o1 + mt * MTB) - gs1);
+                }
+            }
+            if (SAT == 2 && r0.b.z != 0) {
+                // 1D SATs at nodes 0 and Nh-1 of every instance (the record flags the block rows that carry one): lane l
+                // evaluates the term for the warp's tensor rows l (and l + 32), the owning lane fetches it by shuffle
+                const int flags = r0.b.z;
+#pragma unroll 1
+                for (int k = 0; k < 8; k++) {
+                    const bool left = (flags >> k) & 1, right = (flags >> (8 + k)) & 1;
+                    if (!(left | right)) continue;
+                    const int r = (k < 4 ? r0.a.z : r0.a.w - 4) + k;
+                    const int h = (paired && r >= Nh) ? 1 : 0;
+                    // ring_elem is relative to the lane's own tensor row g; here lane l reads tensor row il
+                    const uint32_t o = ring_elem(r);
+                    double sv2[(8 * MT + 31) / 32];
+#pragma unroll
+                    for (int kk = 0; kk < (8 * MT + 31) / 32; kk++) {
+                        const int il = lane + 32 * kk;  // tensor row within the tile
+                        sv2[kk] = 0.0;
+                        if (il < 8 * MT && il < nb) {
+                            const long long row = (long long)b0 + il, inst = paired ? 2 * row + h : row;
+                            const double u = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_u) + o +
+                                                                              (size_t)il * (BX * 8));
+                            double lb = sat_lb, rbv = sat_rb;
+                            if (p.sat.bc_stride != 0) {  // per-instance boundary data
+                                if (left) lb = __ldg(p.sat.bc + inst * p.sat.bc_stride);
+                                if (right) rbv = __ldg(p.sat.bc + inst * p.sat.bc_stride + 1);
+                            }
+                            // (f - a u) / w as in sat1d_left/right, with the division replaced by the reciprocal weight
+                            double v = 0.0;
+                            if (left) {
+                                const double t0 = p.sat.a0 * u;
+                                v += ((p.sat.a0 > 0.0 ? p.sat.a0 * lb : t0) - t0) * sat_iw0;
+                            }
+                            if (right) {
+                                const double tN = p.sat.aN * u;
+                                v -= ((p.sat.aN > 0.0 ? tN : p.sat.aN * rbv) - tN) * sat_iwN;
+                            }
+                            sv2[kk] = v;
+                        }
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) {
+                        const int il = 8 * mt + g;
+                        const double v = __shfl_sync(0xffffffffu, sv2[il >> 5], il & 31);
+                        if (t == (k >> 1)) {
+                            if (k & 1) acc[mt][1] += v;
+                            else acc[mt][0] += v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&bar_empty[st]);    // the ring slots behind this item's window may be refilled
+            mbar_arrive(&fbar_empty[fst]);  // and so may the fragment buffers
+        }
+
+        if (SBP_B3_EXP == 4) {
+            if (acc[0][0] == 1.2345e300) p.dU[0] = acc[MT - 1][1];
+        } else if (OUT == 2) {
+            // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
+            //      one lane stores quad A and quad B as {4 rows x 8*MT instances} boxes ----
+            if (lane == 0) bulk_wait_read<0>();  // the previous boxes of this warp have been read out of the buffer
+            __syncwarp();
+            if (active) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+                    *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
+                fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    if (r0.a.z < Nr) tma_store_2d(&tmap_out, r0.a.z, b0, so);
+                    if (r0.a.w < Nr) tma_store_2d(&tmap_out, r0.a.w, b0, so + 8 * MT * 4);
+                    bulk_commit();
+                }
+            }
+        } else if (active && r0w < N) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const int il = 8 * mt + g;
+                if (il >= nb) continue;
+                double y0 = acc[mt][0], y1 = acc[mt][1];
+                double* yp = p.dU + (long long)(b0 + il) * N + r0w;
+                if (VEC) {  // N even: row r0w + 1 exists
+                    if (p.beta != 0.0) {
+                        const double2 o = *reinterpret_cast<const double2*>(yp);
+                        y0 = fma(p.beta, o.x, y0);
+                        y1 = fma(p.beta, o.y, y1);
+                    }
+                    stg_stream2(yp, y0, y1);
+                } else {
+                    if (p.beta != 0.0) y0 = fma(p.beta, yp[0], y0);
+                    stg_stream1(yp, y0);
+                    if (r0w + 1 < N) {
+                        if (p.beta != 0.0) y1 = fma(p.beta, yp[1], y1);
+                        stg_stream1(yp + 1, y1);
+                    }
+                }
+            }
+        }
+        // ---- next item ----
+        r0 = r1;
+        r1 = r2;
+        if (++c == nch) {
+            c = 0;
+            tile += gridDim.x;
+            b0 += tstepr;
+            offB += stepBr;
+            offB = min(offB, offB - ringBr);
+        }
+        if (++st == nstr) st = 0, phase ^= 1;
+        svst += stvalB, spst += stposB;
+        if (++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
+    }
+    if (OUT == 2 && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
+}
+
+static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out) {
+    const size_t ops = ((size_t)kB3FragStages * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
+    // staging per consumer warp (TMA tensor stores only): 2 quads x instances x 4 rows
+    const size_t staging = out == 2 ? (size_t)kBsrCH * 2 * 8 * MT * 4 * 8 : 0;
+    return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
+}
+static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int out) {
+    return bsr3_smem(op, MT, D, out) + 1024 <= (size_t)ctx->smem_optin;
+}
+
+template <int MT, int SAT, int OUT>
+static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
+    auto kern = k_bsr3<MT, SAT, OUT>;
+    constexpr int TI = 8 * MT;
+    constexpr int THREADS = (kBsrCH + 2) * 32;
+    CUtensorMap tmap, tmap_out;
+    int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
+    if (rc) return rc;
+    rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, TI) : (tmap_out = tmap, SBP_OK);
+    if (rc) return rc;
+    SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (p.B + TI - 1) / TI;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count));
+    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+template <int MT>
+static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out) {
+#define SBP_BSR3_OUT(S)                                                  \
+    switch (out) {                                                       \
+        case 2: return launch_bsr3_k<MT, S, 2>(ctx, p, smem);            \
+        case 1: return launch_bsr3_k<MT, S, 1>(ctx, p, smem);            \
+        default: return launch_bsr3_k<MT, S, 0>(ctx, p, smem);           \
+    }
+    if (sat == 1) { SBP_BSR3_OUT(1) }
+    if (sat == 2) { SBP_BSR3_OUT(2) }
+    SBP_BSR3_OUT(0)
+#undef SBP_BSR3_OUT
+}
+
+// p arrives filled in by launch_bsr (operator, batch view, SAT data); returns false when this kernel does not apply
+bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int out, int32_t* rc) {
+    // SBP_BSR_V3 (read at every launch: the tests switch it): 0 / unset = k_bsr, 1 = this kernel for large batches, 2 = always
+    static int forced_mt = -1, forced_d = 99;
+    if (forced_mt < 0) {
+        const char* e = getenv("SBP_BSR_MT");
+        forced_mt = e ? atoi(e) : 0;
+        e = getenv("SBP_BSR_DEPTH");
+        forced_d = e ? atoi(e) : 99;
+    }
+    const char* ev = getenv("SBP_BSR_V3");
+    const int enabled = ev ? atoi(ev) : 0;  // measured (profiles/r1k_bsr3_notes.txt): no faster than k_bsr -> opt-in
+    if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
+    const long long B = p.B;
+    // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
+    int MT = 8;
+    while (MT > 4 && !bsr3_fits(ctx, op, MT, 1, out)) MT--;
+    while (MT > 4 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT--;
+    if (forced_mt >= 4 && forced_mt <= 8) MT = forced_mt;
+    if (!bsr3_fits(ctx, op, MT, 1, out)) return false;
+    if (enabled != 2 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count / 2) return false;  // small batches: smaller tiles of k_bsr
+    int D = 1;
+    for (int d = 2; d < kB3Stages; d++)
+        if (d <= forced_d && bsr3_fits(ctx, op, MT, d, out)) D = d;
+    p.nbox = op->bsr_nbox[D];
+    p.nst = D + 1;
+    p.item = reinterpret_cast<const int4*>(op->d_bsr_item) + (size_t)D * p.nch * kBsrCH * 2;
+    p.pos = op->d_bsr_pos3 + (size_t)(MT - 1) * (size_t)std::max<int64_t>(op->bsr_frags, 1) * 4;
+    const size_t smem = bsr3_smem(op, MT, D, out);
+    {
+        static int skew = -1;
+        if (skew < 0) {
+            const char* e = getenv("SBP_BSR_SKEW");
+            skew = e ? atoi(e) : 0;
+        }
+        p.skew = skew;
+    }
+    static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d\n",
+                p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out);
+    switch (MT) {
+        case 8: *rc = launch_bsr3_mt<8>(ctx, p, smem, satmode, out); break;
+        case 7: *rc = launch_bsr3_mt<7>(ctx, p, smem, satmode, out); break;
+        case 6: *rc = launch_bsr3_mt<6>(ctx, p, smem, satmode, out); break;
+        case 5: *rc = launch_bsr3_mt<5>(ctx, p, smem, satmode, out); break;
+        default: *rc = launch_bsr3_mt<4>(ctx, p, smem, satmode, out); break;
+    }
+    return true;
+}
+
+}  // namespace sbp

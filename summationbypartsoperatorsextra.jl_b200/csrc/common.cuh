@@ -44,6 +44,7 @@ void set_error(const char* fmt, ...);
 constexpr int kBsrBX = SBP_BSR_BX;     // nodes per TMA box: 4 (mod 16) doubles => conflict-free A-fragment gathers
 constexpr int kBsrCH = SBP_BSR_CH;     // row blocks per chunk
 constexpr int kBsrGroups = SBP_BSR_G;  // consumer groups, alternating chunks
+constexpr int kBsrDepths = 8;          // pipeline depths (chunks of lookahead) the host prepares ring sizes / records for
 static_assert(kBsrBX % 16 == 4, "box rows must be 4 (mod 16) doubles");
 constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
 
@@ -104,13 +105,15 @@ struct sbp_op {
     double* d_bsr_val = nullptr;  // [fragment][32] B-operand fragments (row g, column t)
     int* d_bsr_pos = nullptr;     // [fragment][4] (box - boxlo[chunk]) << 8 | column % kBsrBX
     int* d_bsr_rbmeta = nullptr;  // [nrb][4] {first fragment relative to its chunk, fragments, first row of quad A, of quad B}
-    int* d_bsr_item = nullptr;    // [4 depths][nch * kBsrCH][8] per-row-block record of the consumer warps (see build_bsr)
+    int* d_bsr_item = nullptr;    // [kBsrDepths][nch * kBsrCH][8] per-row-block record of the consumer warps (see build_bsr)
+    int* d_bsr_pos3 = nullptr;    // [8 tile sizes MT][fragment][4] BYTE offsets (box - boxlo[chunk]) * box bytes(MT) + 8 * column (bsr3.cu)
     int* d_bsr_chmeta = nullptr;  // [nch][4] {first fragment, end fragment, lowest box still needed, boxes resident}
     int bsr_nrb = 0;
     int bsr_N = 0;                // row length the block-sparse image works on: N, or 2N for odd N (instance pairs, see build_bsr)
     std::vector<int> bsr_rows;    // host copy: first rows of the two quads of every row block (2 * nrb)
-    int bsr_nbox[4] = {0, 0, 0, 0};  // ring size (boxes) that allows d chunks of lookahead, d = 0..3
-    int bsr_maxf = 0;
+    int bsr_nbox[sbp::kBsrDepths] = {};  // ring size (boxes) that allows d chunks of lookahead, d = 0..kBsrDepths-1
+    int bsr_maxf = 0;             // most fragments of a chunk
+    int bsr_maxnf = 0;            // most fragments of a row block
     int64_t bsr_frags = 0;
     // advection bundles
     const sbp_op* inner = nullptr;
@@ -173,6 +176,9 @@ int32_t launch_sparse(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* 
                       double beta, const sbp_op* adv, const double* g, int64_t g_stride, double* quantities);
 bool bsr_available(const sbp_ctx* ctx, const sbp_op* op);
 bool bsr_can_run(const sbp_op* op, const double* U);
+struct BsrParams;
+// bsr3.cu: lean consumer loop (operator fragments prefetched from L2 into registers); false = not applicable, use k_bsr
+bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int out, int32_t* rc);
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
                    const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat);
 int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V, int64_t B,

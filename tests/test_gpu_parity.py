@@ -214,12 +214,21 @@ def test_apply_large_dense(ctx, N, B):
 
 
 # ---- K2: structurally sparse operators ---------------------------------------------------------------------------
-@pytest.fixture(params=["bsr", "sell"])
+@pytest.fixture(params=["bsr3", "bsr", "sell"])
 def sparse_kernel(request, monkeypatch):
-    """both sparse kernels: block-sparse DMMA (bsr.cu, default) and the scalar row-blocked SELL kernel (sparse.cu);
-    SBP_SPARSE_KERNEL is read by sbp_op_sparse_create at every upload"""
-    monkeypatch.setenv("SBP_SPARSE_KERNEL", request.param)
-    return {"bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
+    """all sparse kernels: block-sparse DMMA with the lean consumer loop (bsr3.cu, default for large batches; forced
+    here for every batch size), its first generation (bsr.cu, small batches) and the scalar row-blocked SELL kernel
+    (sparse.cu); SBP_SPARSE_KERNEL is read by sbp_op_sparse_create at every upload, SBP_BSR_V3 at every launch"""
+    monkeypatch.setenv("SBP_SPARSE_KERNEL", "sell" if request.param == "sell" else "bsr")
+    monkeypatch.setenv("SBP_BSR_V3", "2" if request.param == "bsr3" else "0")
+    return {"bsr3": "bsr_dmma", "bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
+
+
+@pytest.fixture(params=[2, 0])
+def bsr_generation(request, monkeypatch):
+    """block-sparse kernel generation: 2 = bsr3.cu forced, 0 = bsr.cu"""
+    monkeypatch.setenv("SBP_BSR_V3", str(request.param))
+    return request.param
 
 
 @pytest.mark.parametrize("order,N", [(2, 101), (4, 101), (4, 102), (4, 400), (2, 1500)])
@@ -571,7 +580,7 @@ def test_config5_sized_dense_gemm_checksum(ctx):
 # ---- odd N on the block-sparse kernel: instance PAIRS multiplied by diag(D, D) (csrc/api.cu build_bsr) ------------
 @pytest.mark.parametrize("n1", [5, 7, 9])  # N = 25, 49, 81: odd
 @pytest.mark.parametrize("B", [1, 2, 65, 130, 1027])
-def test_rhs_advection2d_odd_N(ctx, n1, B):
+def test_rhs_advection2d_odd_N(ctx, n1, B, bsr_generation):
     D = _scattered_mfsbp(n1, seed=3)
     assert D.N % 2 == 1
     a = (0.7, -1.0)
@@ -594,7 +603,7 @@ def test_rhs_advection2d_odd_N(ctx, n1, B):
 
 @pytest.mark.parametrize("N", [21, 101, 103])
 @pytest.mark.parametrize("B", [1, 2, 77, 1030])
-def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B):
+def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B, bsr_generation):
     D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
     D.storage = "sparse"
     Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)

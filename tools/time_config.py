@@ -81,7 +81,8 @@ def main():
             S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
     elif args.workload in ("config3", "config1b"):
         if args.workload == "config3":  # 2D MFSBP advection RHS with SAT on a jittered 36x36 cloud
-            n1, B = 36, 65536
+            n1 = args.n if args.n != 64 else 36  # --n: grid points per direction (N = n1^2), batch scaled to ~85 M DOF
+            B = 65536 if n1 == 36 else (65536 * 1296 // (n1 * n1)) // 64 * 64
             rng = np.random.default_rng(0)
             D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, n1))
             nodes = D2.grid.copy()
