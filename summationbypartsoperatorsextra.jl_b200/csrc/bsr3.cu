@@ -27,9 +27,14 @@
 #include "bsr.cuh"
 
 // -DSBP_B3_EXP=n: what-if builds for bottleneck hunting (WRONG RESULTS): 1 = no DMMA, 2 = no A-operand loads inside the chain,
-// 3 = no TMA box loads, 4 = no output
+// 3 = no TMA box loads, 4 = no output, 5 = all tiles store to the rows of tile 0, 6 = all tiles load the rows of tile 0
+// (7 = staging + fence but no TMA store, 8 = TMA stores without staging/fence, 9 = accumulators consumed + fence, no stores:
+// measured in session 4, code removed)
 #ifndef SBP_B3_EXP
 #define SBP_B3_EXP 0
+#endif
+#ifndef SBP_B3_DEFER
+#define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
 
 namespace sbp {
@@ -64,13 +69,17 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
     }
 }
 
-template <int MT, int SAT, int OUT>
-__global__ void __launch_bounds__((kBsrCH + 2) * 32)
+// CW consumer warps (8 or 12) share the row blocks of the item stream round-robin: block k = 8 * item + slot belongs to warp
+// k % CW.  CW = 8: a warp keeps its slot and has a block in every item; CW = 12: three consumer warps per scheduler, a warp
+// has a block in two out of three items (it still passes every item's "full" barrier, in order).
+template <int MT, int SAT, int OUT, int CW>
+__global__ void __launch_bounds__((CW + 2) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
     constexpr int TI = 8 * MT;
-    constexpr int CONS = kBsrCH;               // consumer warps: one row block of the chunk each
+    constexpr int CONS = CW;                   // consumer warps
+    static_assert(CW >= kBsrCH && CW < 2 * kBsrCH, "a consumer warp has at most one row block per item");
     constexpr int BOX = TI * BX;               // doubles per box
     constexpr uint32_t BOXB = BOX * 8;         // bytes per box
     constexpr uint32_t MTB = 8 * BX * 8;       // byte distance between the m-tiles of a lane
@@ -92,8 +101,8 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
             mbar_init(&bar_full[s], 1);      // the box producer's arrive.expect_tx
-            mbar_init(&bar_empty[s], CONS);  // lane 0 of every consumer warp
-        }
+            mbar_init(&bar_empty[s], CONS);  // lane 0 of EVERY consumer warp, block in this item or not: a stage that could be
+        }                                    // refilled without a warp's arrival might lap that warp's phase tracking
         for (int s = 0; s < kB3FragStages; s++) {
             mbar_init(&fbar_full[s], 1);
             mbar_init(&fbar_empty[s], CONS);
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
                             asm volatile(
                                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
                                 "{%2, %3}], [%4];\n" ::"r"(dst),
-                                "l"(&tmap), "r"(x), "r"(b0), "r"(bar)
+                                "l"(&tmap), "r"(x), "r"(SBP_B3_EXP == 6 ? 0 : b0), "r"(bar)
                                 : "memory");
                             if (++slot == nbox) slot = 0;
                         }
@@ -179,14 +188,13 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
         int4 b;      // {ring slot of the chunk's lowest box, lowest box, 1D SAT flags, -}
         double2 sb;  // 2D SAT coefficients of the lane's two rows (0: none)
     };
-    const int4* const items = p.item + 2 * warp;
-    const double2* const sbs = reinterpret_cast<const double2*>(p.rb_bdiag) + 4 * warp + t;
-    auto load_rec = [&](int c) {
+    const double2* const sbs = reinterpret_cast<const double2*>(p.rb_bdiag) + t;
+    auto load_rec = [&](int rb) {  // rb = 8 * chunk + slot
         Rec r;
-        r.a = __ldg(items + c * (2 * kBsrCH));
-        r.b = __ldg(items + c * (2 * kBsrCH) + 1);
+        r.a = __ldg(p.item + 2 * rb);
+        r.b = __ldg(p.item + 2 * rb + 1);
         r.sb = make_double2(0.0, 0.0);
-        if (SAT == 1) r.sb = __ldg(sbs + c * (4 * kBsrCH));
+        if (SAT == 1) r.sb = __ldg(sbs + 4 * rb);
         return r;
     };
 
@@ -195,8 +203,19 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
     uint32_t offB = 0;                            // ring offset of the tile's box 0 (bytes)
     const uint32_t stepB = (uint32_t)stepb * BOXB;
     const int ntl = (int)ntiles, tstep = gridDim.x * TI, Bi = (int)p.B;
-    Rec r0 = load_rec(0), r1 = load_rec(1 % p.nch);
-    int c2 = 2 % p.nch;
+    // position of a warp's next row block in the (periodic) record array: chunk pc, slot ps; the one after it is CW blocks on
+    int ps = warp % kBsrCH, pc = (warp / kBsrCH) % p.nch;
+    auto advance = [&]() {
+        const int q = ps + CW;
+        ps = q & (kBsrCH - 1);
+        pc += q / kBsrCH;
+        while (pc >= p.nch) pc -= p.nch;
+    };
+    Rec r0 = load_rec(kBsrCH * pc + ps);
+    advance();
+    Rec r1 = load_rec(kBsrCH * pc + ps);
+    advance();
+    int skip = warp / kBsrCH, myslot = warp % kBsrCH;  // items to pass before this warp's next block; its slot there
     double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0;
     if (SAT == 2) {
         sat_iw0 = 1.0 / p.sat.w0, sat_iwN = 1.0 / p.sat.wN;
@@ -221,9 +240,38 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
         while (clock64() - t0 < p.skew) {
         }
     }
-    while (tile < ntlr) {
-        const Rec r2 = load_rec(c2);  // record of the item after the next one
-        if (++c2 == nch) c2 = 0;
+    // DEFER: the results of a block leave the registers one block later, after the NEXT chain has been issued (two accumulator
+    // sets, the loop is unrolled by two for static register indices): the warp never waits for its own DMMAs to complete, and
+    // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
+    constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0;
+    double accs[DEFER ? 2 : 1][MT][2];
+    int pv_rowA = 0, pv_rowB = 0, pv_b0 = 0, pv_state = 0;  // deferred block: rows of its quads, first tensor row, 1 = pending | 2 = scale | 4 = set
+    // staging + TMA stores of one block's accumulators
+    auto emit = [&](double (&a)[MT][2], int rowA, int rowB, int yb0, bool scale) {
+        if (lane == 0) bulk_wait_read<0>();  // the previous boxes of this warp have been read out of the buffer
+        __syncwarp();
+        if (scale) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) a[mt][0] *= p.alpha, a[mt][1] *= p.alpha;
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(a[mt][0], a[mt][1]);
+        fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+            const int yo = SBP_B3_EXP == 5 ? 0 : yb0;  // what-if 5: every tile writes the rows of tile 0 (L2-resident output)
+            if (rowA < Nr) tma_store_2d(&tmap_out, rowA, yo, so);
+            if (rowB < Nr) tma_store_2d(&tmap_out, rowB, yo, so + 8 * MT * 4);
+            bulk_commit();
+        }
+    };
+    while (true) {
+#pragma unroll
+     for (int hf = 0; hf < (DEFER ? 2 : 1); hf++) {
+      if (tile >= ntlr) goto done;
+      if (CW == kBsrCH || skip == 0) {
+        const Rec r2 = load_rec(kBsrCH * pc + ps);  // record of the block after the next one
+        advance();
         const int nf = r0.a.y;
         const bool active = r0.a.z < Nr;  // padding records of the last chunk carry rows >= N and no fragments
         // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
@@ -243,7 +291,7 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
             if (mask & 1) gs0 = __ldg(p.g + n0);
             if (mask & 2) gs1 = __ldg(p.g + n1);
         }
-        double acc[MT][2];
+        double(&acc)[MT][2] = accs[DEFER ? hf : 0];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
         // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
@@ -294,8 +342,12 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
         }
 
         const int nb = min(Bir - b0, TI);
+        // blocks that carry SAT terms finish their accumulators now (the terms read the ring); for the others a deferred
+        // epilogue also takes over the scaling by alpha
+        const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
+        const bool scale_later = DEFER && scale_needed && !sat_block;
         if (active) {
-            if (scale_needed) {
+            if (scale_needed && !scale_later) {
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) acc[mt][0] *= p.alpha, acc[mt][1] *= p.alpha;
             }
@@ -378,23 +430,14 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
 
         if (SBP_B3_EXP == 4) {
             if (acc[0][0] == 1.2345e300) p.dU[0] = acc[MT - 1][1];
+        } else if (DEFER) {
+            if (pv_state & 1) emit(accs[DEFER ? hf ^ 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
+            pv_rowA = r0.a.z, pv_rowB = r0.a.w, pv_b0 = b0;
+            pv_state = (active ? 1 : 0) | (scale_later ? 2 : 0) | (hf ? 4 : 0);
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
             //      one lane stores quad A and quad B as {4 rows x 8*MT instances} boxes ----
-            if (lane == 0) bulk_wait_read<0>();  // the previous boxes of this warp have been read out of the buffer
-            __syncwarp();
-            if (active) {
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++)
-                    *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
-                fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    if (r0.a.z < Nr) tma_store_2d(&tmap_out, r0.a.z, b0, so);
-                    if (r0.a.w < Nr) tma_store_2d(&tmap_out, r0.a.w, b0, so + 8 * MT * 4);
-                    bulk_commit();
-                }
-            }
+            if (active) emit(acc, r0.a.z, r0.a.w, b0, false);
         } else if (active && r0w < N) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
@@ -419,9 +462,21 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
                 }
             }
         }
-        // ---- next item ----
         r0 = r1;
         r1 = r2;
+        skip = (myslot + CW) / kBsrCH - 1;
+        myslot = (myslot + CW) & (kBsrCH - 1);
+      } else {
+        // no block of this item: observe its boxes (later windows reach back into them) and release it at once
+        mbar_wait(&fbar_full[fst], fphase);
+        mbar_wait(&bar_full[st], phase);
+        if (lane == 0) {
+            mbar_arrive(&bar_empty[st]);
+            mbar_arrive(&fbar_empty[fst]);
+        }
+        skip--;
+      }
+        // ---- next item ----
         if (++c == nch) {
             c = 0;
             tile += gridDim.x;
@@ -432,25 +487,31 @@ __global__ void __launch_bounds__((kBsrCH + 2) * 32)
         if (++st == nstr) st = 0, phase ^= 1;
         svst += stvalB, spst += stposB;
         if (++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
+     }
+    }
+done:
+    if (DEFER && (pv_state & 1)) {  // the last block of this warp
+        if (pv_state & 4) emit(accs[DEFER ? 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
+        else emit(accs[0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
     }
     if (OUT == 2 && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
 }
 
-static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out) {
+static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out, int cw) {
     const size_t ops = ((size_t)kB3FragStages * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
     // staging per consumer warp (TMA tensor stores only): 2 quads x instances x 4 rows
-    const size_t staging = out == 2 ? (size_t)kBsrCH * 2 * 8 * MT * 4 * 8 : 0;
+    const size_t staging = out == 2 ? (size_t)cw * 2 * 8 * MT * 4 * 8 : 0;
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
-static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int out) {
-    return bsr3_smem(op, MT, D, out) + 1024 <= (size_t)ctx->smem_optin;
+static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int out, int cw) {
+    return bsr3_smem(op, MT, D, out, cw) + 1024 <= (size_t)ctx->smem_optin;
 }
 
-template <int MT, int SAT, int OUT>
+template <int MT, int SAT, int OUT, int CW>
 static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr3<MT, SAT, OUT>;
+    auto kern = k_bsr3<MT, SAT, OUT, CW>;
     constexpr int TI = 8 * MT;
-    constexpr int THREADS = (kBsrCH + 2) * 32;
+    constexpr int THREADS = (CW + 2) * 32;
     CUtensorMap tmap, tmap_out;
     int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
     if (rc) return rc;
@@ -466,12 +527,12 @@ static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
 }
 
 template <int MT>
-static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out) {
-#define SBP_BSR3_OUT(S)                                                  \
-    switch (out) {                                                       \
-        case 2: return launch_bsr3_k<MT, S, 2>(ctx, p, smem);            \
-        case 1: return launch_bsr3_k<MT, S, 1>(ctx, p, smem);            \
-        default: return launch_bsr3_k<MT, S, 0>(ctx, p, smem);           \
+static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out, int cw) {
+#define SBP_BSR3_OUT(S)                                                                                    \
+    switch (out) {                                                                                         \
+        case 2: return cw == 12 ? launch_bsr3_k<MT, S, 2, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 2, 8>(ctx, p, smem); \
+        case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, 8>(ctx, p, smem); \
+        default: return launch_bsr3_k<MT, S, 0, 8>(ctx, p, smem);                                          \
     }
     if (sat == 1) { SBP_BSR3_OUT(1) }
     if (sat == 2) { SBP_BSR3_OUT(2) }
@@ -492,22 +553,28 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const char* ev = getenv("SBP_BSR_V3");
     const int enabled = ev ? atoi(ev) : 0;  // measured (profiles/r1k_bsr3_notes.txt): no faster than k_bsr -> opt-in
     if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
+    static int forced_cw = -1;
+    if (forced_cw < 0) {
+        const char* e = getenv("SBP_BSR_CW");
+        forced_cw = e ? atoi(e) : 8;
+    }
+    const int cw = (forced_cw == 12 && out != 0) ? 12 : 8;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;
-    while (MT > 4 && !bsr3_fits(ctx, op, MT, 1, out)) MT--;
+    while (MT > 4 && !bsr3_fits(ctx, op, MT, 1, out, cw)) MT--;
     while (MT > 4 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT--;
     if (forced_mt >= 4 && forced_mt <= 8) MT = forced_mt;
-    if (!bsr3_fits(ctx, op, MT, 1, out)) return false;
+    if (!bsr3_fits(ctx, op, MT, 1, out, cw)) return false;
     if (enabled != 2 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count / 2) return false;  // small batches: smaller tiles of k_bsr
     int D = 1;
     for (int d = 2; d < kB3Stages; d++)
-        if (d <= forced_d && bsr3_fits(ctx, op, MT, d, out)) D = d;
+        if (d <= forced_d && bsr3_fits(ctx, op, MT, d, out, cw)) D = d;
     p.nbox = op->bsr_nbox[D];
     p.nst = D + 1;
     p.item = reinterpret_cast<const int4*>(op->d_bsr_item) + (size_t)D * p.nch * kBsrCH * 2;
     p.pos = op->d_bsr_pos3 + (size_t)(MT - 1) * (size_t)std::max<int64_t>(op->bsr_frags, 1) * 4;
-    const size_t smem = bsr3_smem(op, MT, D, out);
+    const size_t smem = bsr3_smem(op, MT, D, out, cw);
     {
         static int skew = -1;
         if (skew < 0) {
@@ -518,14 +585,14 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     }
     static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
     if (verbose)
-        fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d\n",
-                p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out);
+        fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d cw=%d\n",
+                p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out, cw);
     switch (MT) {
-        case 8: *rc = launch_bsr3_mt<8>(ctx, p, smem, satmode, out); break;
-        case 7: *rc = launch_bsr3_mt<7>(ctx, p, smem, satmode, out); break;
-        case 6: *rc = launch_bsr3_mt<6>(ctx, p, smem, satmode, out); break;
-        case 5: *rc = launch_bsr3_mt<5>(ctx, p, smem, satmode, out); break;
-        default: *rc = launch_bsr3_mt<4>(ctx, p, smem, satmode, out); break;
+        case 8: *rc = launch_bsr3_mt<8>(ctx, p, smem, satmode, out, cw); break;
+        case 7: *rc = launch_bsr3_mt<7>(ctx, p, smem, satmode, out, cw); break;
+        case 6: *rc = launch_bsr3_mt<6>(ctx, p, smem, satmode, out, cw); break;
+        case 5: *rc = launch_bsr3_mt<5>(ctx, p, smem, satmode, out, cw); break;
+        default: *rc = launch_bsr3_mt<4>(ctx, p, smem, satmode, out, cw); break;
     }
     return true;
 }
