@@ -436,6 +436,9 @@ def run_native(args):
 
     # ---- end-to-end through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region ----
     e2e_steps = max(2, min(args.steps, 5))
+    # host buffers and the copy-issuing thread on the GPU's NUMA node (restored below: the CPU baseline uses every core)
+    affinity0 = os.sched_getaffinity(0)
+    e2e_cpus = ctx.bind_host_to_gpu_numa()
     hU, hY = ctx.pinned_empty((B, N)), ctx.pinned_empty((B, N))
     hU[:] = np.random.default_rng(rank).uniform(-1, 1, (B, N))
 
@@ -456,6 +459,7 @@ def run_native(args):
     e2e_s = float(te.item())
     checksum = float(hY[:: max(1, B // 1024)].sum())
     ctx.free_pinned(hU), ctx.free_pinned(hY)
+    os.sched_setaffinity(0, affinity0)
 
     try:
         c5 = config5_sharded(torch, S, ctx, dist, rank, world, dev) if not args.no_extra else None
@@ -505,6 +509,7 @@ def run_native(args):
         "e2e": {"value": world * dofs_step * e2e_steps / e2e_s / 1e9, "unit": "GDOF/s",
                 "h2d_bytes_per_step": int(dofs_step * 8), "d2h_bytes_per_step": int(dofs_step * 8),
                 "steps": e2e_steps, "api": "sbp_apply_host (pinned host buffers, chunked H2D/compute/D2H overlap)",
+                "host_numa_cpus": len(e2e_cpus),
                 "checksum": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,

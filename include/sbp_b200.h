@@ -80,6 +80,9 @@ int32_t sbp_ctx_device_info(sbp_ctx* ctx, int32_t* sm_count, int64_t* l2_bytes, 
                             int64_t* global_bytes);
 /* number of kernels this ctx has launched since creation (for harness accounting) */
 int64_t sbp_ctx_launch_count(sbp_ctx* ctx);
+/* PCI bus id of the ctx's device ("0000:1b:00.0", lower case, NUL-terminated; len >= 16): lets the host side place its pinned
+ * buffers and threads on the GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist) before calling the *_host entry points */
+int32_t sbp_ctx_pci_bus_id(sbp_ctx* ctx, char* buf, int32_t len);
 
 /* ---- memory ---------------------------------------------------------------------------- */
 int32_t sbp_malloc(sbp_ctx* ctx, size_t bytes, void** dptr);
@@ -191,6 +194,20 @@ int32_t sbp_rhs_advection2d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
  * instance at bc + b*bc_stride.  quantities as above (src/conservation_laws/analysis_callback.jl:136-173). */
 int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B,
                             const double* bc, int64_t bc_stride, double* quantities);
+
+/* Runge-Kutta stage updates riding on the RHS pass (device-resident time stepping: SSPRK53 of
+ * examples/RBF_FSBP_advection.jl:45-51, the low-storage schemes of examples/RBF_MFSBP_advection.jl:22-27):
+ *     Unext = ca*U + cb*Uextra + ch*RHS(U),
+ * RHS as in sbp_rhs_advection2d / sbp_rhs_advection1d (same g / bc arguments).  Uextra may be NULL (cb ignored) and may
+ * alias Unext; Unext must not alias U.  On the block-sparse kernel the update is part of the RHS kernel (U's own rows are
+ * already on chip: 16-24 B/DOF per stage instead of 16 + 24..32); other kernel families evaluate the RHS into a library
+ * buffer and combine in one pass. */
+int32_t sbp_rhs_advection2d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext, const double* U, int64_t B,
+                                  const double* g, int64_t g_stride, double ca, double cb, const double* Uextra,
+                                  double ch);
+int32_t sbp_rhs_advection1d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext, const double* U, int64_t B,
+                                  const double* bc, int64_t bc_stride, double ca, double cb, const double* Uextra,
+                                  double ch);
 
 /* Y = a*X + b*Y + c*Z elementwise over n doubles (Z may be NULL): stage updates of the explicit
  * Runge-Kutta schemes the examples use (SSPRK53, RDPK3SpFSAL49) so that a step never leaves the device. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "sbp_ctx_launch_count": (c_i64, [c_void_p]),
     "sbp_malloc": (c_i32, [c_void_p, c_size_t, P(c_void_p)]),
     "sbp_free": (c_i32, [c_void_p, c_void_p]),
+    "sbp_ctx_pci_bus_id": (c_i32, [c_void_p, C.c_char_p, c_i32]),
     "sbp_host_alloc": (c_i32, [c_size_t, P(c_void_p)]),
     "sbp_host_free": (c_i32, [c_void_p]),
     "sbp_memcpy_h2d": (c_i32, [c_void_p, c_void_p, c_void_p, c_size_t]),
@@ -89,6 +90,10 @@ SIGNATURES = {
     "sbp_scale_by_mass_matrix": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_i32]),
     "sbp_rhs_advection2d": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "sbp_rhs_advection1d": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
+    "sbp_rhs_advection2d_stage": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_dbl, c_dbl,
+                                          c_void_p, c_dbl]),
+    "sbp_rhs_advection1d_stage": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_dbl, c_dbl,
+                                          c_void_p, c_dbl]),
     "sbp_axpbypcz": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, c_dbl]),
     "sbp_lincomb": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, c_dbl, c_dbl]),
     "sbp_comm_unique_id": (c_i32, [c_void_p]),

@@ -83,12 +83,33 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
         return ent[0]
 
     def boundary_values(self, t: float) -> np.ndarray:
-        """g_j = bc(x_j, t) at inflow nodes (0 elsewhere) -- the data `set_bc!` writes into tmp1 (:65-66)."""
+        """g_j = bc(x_j, t) at inflow nodes (0 elsewhere) -- the data `set_bc!` writes into tmp1 (:65-66).  A boundary
+        function that accepts coordinate arrays (x = (xs, ys)) is evaluated once for all inflow nodes, any other one
+        node by node."""
         g = np.zeros(self.derivative.N)
         nodes = self.derivative.grid
-        for j in self.inflow_nodes:
-            g[j] = self.bc(nodes[j], t)
+        idx = np.asarray(self.inflow_nodes, dtype=np.int64)
+        if idx.size == 0:
+            return g
+        vals = None
+        if getattr(self, "_bc_vectorised", True):
+            try:
+                v = np.asarray(self.bc(nodes[idx].T, t), dtype=np.float64)
+                j0 = int(idx[0])
+                if v.shape == (idx.size,) and v[0] == float(self.bc(nodes[j0], t)):
+                    vals = v
+            except Exception:
+                pass
+            self._bc_vectorised = vals is not None
+        if vals is None:
+            vals = [self.bc(nodes[j], t) for j in idx]
+        g[idx] = vals
         return g
+
+    def boundary_table(self, ctx: Context, times) -> RawBuffer:
+        """Boundary data of several evaluation times in one upload: row k = boundary_values(times[k]) (N doubles)."""
+        tab = np.stack([self.boundary_values(float(t)) for t in times]) if len(times) else np.zeros((0, self.derivative.N))
+        return ctx.upload_array(tab)
 
     def _device_g(self, ctx: Context, t: float):
         ent = self._g_cache.get(id(ctx))
@@ -117,6 +138,29 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
         check(ctx._lib.sbp_rhs_advection2d(ctx.handle, op.handle, _ptr(du.ptr), _ptr(u.ptr), u.B, _ptr(gptr),
                                            gstride, _ptr(quantities.ptr) if quantities is not None else None))
         return None
+
+    def stage(self, unext: DeviceBatch, u: DeviceBatch, t: float, ca: float, ch: float, cb: float = 0.0,
+              extra: DeviceBatch | None = None, g: DeviceBatch | None = None, gptr: int | None = None):
+        """Runge-Kutta stage update riding on the RHS pass: unext = ca*u + cb*extra + ch*semi(u, t)
+        (sbp_rhs_advection2d_stage; `extra` may be `unext` itself, `unext` must not be `u`).  `gptr`: device address
+        of boundary data shared by the batch that is already resident (a row of `boundary_table`)."""
+        N = self.derivative.N
+        if u.N != N or unext.shape != u.shape or (extra is not None and extra.shape != u.shape):
+            raise DimensionMismatch("unext, u, extra and the operator differ in size")
+        ctx = u.ctx
+        op = self.device_op(ctx)
+        if gptr is not None:
+            gstride = 0
+        elif g is None:
+            gptr, gstride = self._device_g(ctx, float(t)).ptr, 0
+        else:
+            if g.shape != u.shape:
+                raise DimensionMismatch("per-instance boundary data must have the shape of u")
+            gptr, gstride = g.ptr, N
+        check(ctx._lib.sbp_rhs_advection2d_stage(ctx.handle, op.handle, _ptr(unext.ptr), _ptr(u.ptr), u.B, _ptr(gptr),
+                                                 gstride, float(ca), float(cb),
+                                                 _ptr(extra.ptr) if extra is not None else None, float(ch)))
+        return unext
 
     def __repr__(self):
         return ("Semidiscretization of the linear advection equation\n"
@@ -176,6 +220,34 @@ class VariableLinearAdvectionNonperiodicSemidiscretization(AbstractSemidiscretiz
         check(ctx._lib.sbp_rhs_advection1d(ctx.handle, op.handle, _ptr(du.ptr), _ptr(u.ptr), u.B, _ptr(bptr), bstride,
                                            _ptr(quantities.ptr) if quantities is not None else None))
         return None
+
+    def boundary_table(self, ctx: Context, times) -> RawBuffer:
+        """Boundary data of several evaluation times in one upload: row k = [left_bc(t_k), right_bc(t_k)]."""
+        tab = np.array([[self.left_bc(float(t)), self.right_bc(float(t))] for t in times], dtype=np.float64).reshape(-1, 2)
+        return ctx.upload_array(tab)
+
+    def stage(self, unext: DeviceBatch, u: DeviceBatch, t: float, ca: float, ch: float, cb: float = 0.0,
+              extra: DeviceBatch | None = None, bc: DeviceBatch | None = None, gptr: int | None = None):
+        """Runge-Kutta stage update riding on the RHS pass: unext = ca*u + cb*extra + ch*semi(u, t)
+        (sbp_rhs_advection1d_stage; `extra` may be `unext` itself, `unext` must not be `u`).  `gptr`: device address
+        of resident boundary data [left, right] shared by the batch (a row of `boundary_table`)."""
+        N = self.derivative.N
+        if u.N != N or unext.shape != u.shape or (extra is not None and extra.shape != u.shape):
+            raise DimensionMismatch("unext, u, extra and the operator differ in size")
+        ctx = u.ctx
+        op = self.device_op(ctx)
+        if gptr is not None:
+            bptr, bstride = gptr, 0
+        elif bc is None:
+            bptr, bstride = self._device_bc(ctx, float(t)).ptr, 0
+        else:
+            if bc.shape != (u.B, 2):
+                raise DimensionMismatch("per-instance boundary data must be (B, 2)")
+            bptr, bstride = bc.ptr, 2
+        check(ctx._lib.sbp_rhs_advection1d_stage(ctx.handle, op.handle, _ptr(unext.ptr), _ptr(u.ptr), u.B, _ptr(bptr),
+                                                 bstride, float(ca), float(cb),
+                                                 _ptr(extra.ptr) if extra is not None else None, float(ch)))
+        return unext
 
 
 def analyze_quantities(semi, du: DeviceBatch, u: DeviceBatch, p=None, t: float = 0.0, **kw) -> np.ndarray:
@@ -254,31 +326,61 @@ _SSPRK53 = dict(
 
 
 def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None = None) -> DeviceBatch:
-    """Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive=false)`, examples/RBF_FSBP_advection.jl:45-51) with
-    every stage update one pass on the device (sbp_lincomb); returns the final state."""
+    """Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive=false)`, examples/RBF_FSBP_advection.jl:45-51), device
+    resident: every stage is ONE call -- the stage update rides on the RHS pass (`semi.stage`, sbp_rhs_advection*_stage:
+    104 B/DOF per step on the block-sparse kernel instead of 80 + 144 with separate RHS and update passes).  Semi-
+    discretizations without a `stage` method take the RHS + `lincomb_` route.  Returns the final state."""
     k = _SSPRK53
     u: DeviceBatch = prob.u0
     semi, p = prob.f, prob.p
     t, tend = float(prob.tspan[0]), float(prob.tspan[1])
-    du, u1, u2, u3 = u.similar(), u.similar(), u.similar(), u.similar()
+    u1, u2, u3 = u.similar(), u.similar(), u.similar()
     u = u.copy()
+    fused = hasattr(semi, "stage")
+    du = u.similar() if (callback is not None or not fused) else None
     step = 0
     if callback is not None and callback.should_fire(step, t, False):
         callback(du, u, p, t)
+    table, trow, tstride = None, 0, 0  # boundary data of the next steps' stage times, uploaded 64 steps at a time
+    cs = (0.0, k["c1"], k["c2"], k["c3"], k["c4"])
     while t < tend - 1e-14:
         h = min(dt, tend - t)
-        semi(du, u, p, t)
-        u1.lincomb_(1.0, u, k["b10"] * h, du)                                 # u1 = u + b10 h f(u)
-        semi(du, u1, p, t + k["c1"] * h)
-        u2.lincomb_(1.0, u1, k["b21"] * h, du)                                # u2 = u1 + b21 h f(u1)
-        semi(du, u2, p, t + k["c2"] * h)
-        u3.lincomb_(k["a30"], u, k["a32"], u2, k["b32"] * h, du)              # u3 = a30 u + a32 u2 + b32 h f(u2)
-        semi(du, u3, p, t + k["c3"] * h)
-        u1.lincomb_(k["a40"], u, k["a43"], u3, k["b43"] * h, du)              # u4 (in u1)
-        semi(du, u1, p, t + k["c4"] * h)
-        u.lincomb_(k["a52"], u2, k["a54"], u1, k["b54"] * h, du)              # u5
+        if fused:
+            gp = [None] * 5
+            if hasattr(semi, "boundary_table"):
+                if table is None or trow + 5 > tstride:
+                    if table is not None:
+                        table[0].free()
+                    times, tt = [], t
+                    while tt < tend - 1e-14 and len(times) < 5 * 64:
+                        hh = min(dt, tend - tt)
+                        times += [tt + c * hh for c in cs]
+                        tt += hh
+                    buf = semi.boundary_table(u.ctx, times)
+                    table, trow, tstride = (buf, buf.nbytes // max(len(times), 1)), 0, len(times)
+                gp = [table[0].ptr + (trow + i) * table[1] for i in range(5)]
+                trow += 5
+            semi.stage(u1, u, t, 1.0, k["b10"] * h, gptr=gp[0])                                   # u1 = u + b10 h f(u)
+            semi.stage(u2, u1, t + k["c1"] * h, 1.0, k["b21"] * h, gptr=gp[1])                    # u2 = u1 + b21 h f(u1)
+            semi.stage(u3, u2, t + k["c2"] * h, k["a32"], k["b32"] * h, k["a30"], u, gptr=gp[2])  # u3 = a30 u + a32 u2 + b32 h f(u2)
+            semi.stage(u1, u3, t + k["c3"] * h, k["a43"], k["b43"] * h, k["a40"], u, gptr=gp[3])  # u4 (in u1)
+            semi.stage(u, u1, t + k["c4"] * h, k["a54"], k["b54"] * h, k["a52"], u2, gptr=gp[4])  # u5 = a52 u2 + a54 u4 + b54 h f(u4)
+        else:
+            semi(du, u, p, t)
+            u1.lincomb_(1.0, u, k["b10"] * h, du)
+            semi(du, u1, p, t + k["c1"] * h)
+            u2.lincomb_(1.0, u1, k["b21"] * h, du)
+            semi(du, u2, p, t + k["c2"] * h)
+            u3.lincomb_(k["a30"], u, k["a32"], u2, k["b32"] * h, du)
+            semi(du, u3, p, t + k["c3"] * h)
+            u1.lincomb_(k["a40"], u, k["a43"], u3, k["b43"] * h, du)
+            semi(du, u1, p, t + k["c4"] * h)
+            u.lincomb_(k["a52"], u2, k["a54"], u1, k["b54"] * h, du)
         t += h
         step += 1
         if callback is not None and callback.should_fire(step, t, t >= tend - 1e-14):
             callback(du, u, p, t)
+    if table is not None:
+        u.ctx.synchronize()
+        table[0].free()
     return u

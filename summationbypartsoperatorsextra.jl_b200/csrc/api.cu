@@ -667,6 +667,7 @@ int32_t sbp_ctx_destroy(sbp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage_buf) cudaFree(ctx->stage_buf);
     for (int s = 0; s < 2; s++) {
         for (int k = 0; k < 2; k++)
             if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
@@ -705,6 +706,14 @@ int32_t sbp_free(sbp_ctx* ctx, void* dptr) {
     SBP_CUDA(cudaFree(dptr));
     return SBP_OK;
 }
+int32_t sbp_ctx_pci_bus_id(sbp_ctx* ctx, char* buf, int32_t len) {
+    SBP_REQUIRE(ctx && buf && len >= 16, SBP_EINVAL, "sbp_ctx_pci_bus_id: need a ctx and a buffer of at least 16 bytes");
+    SBP_CUDA(cudaDeviceGetPCIBusId(buf, len, ctx->device));
+    for (char* c = buf; *c; c++)
+        if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    return SBP_OK;
+}
+
 int32_t sbp_host_alloc(size_t bytes, void** hptr) {
     SBP_REQUIRE(hptr, SBP_EINVAL, "null output");
     SBP_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
@@ -1119,6 +1128,83 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     if (rc) return rc;
     if (fused && quantities == nullptr) return SBP_OK;
     return launch_adv1d_epilogue(ctx, op, dU, U, B, bc, bc_stride, quantities, !fused);
+}
+
+// ---- Runge-Kutta stage updates fused into the RHS pass ----------------------------------------------
+// Unext <- ca * U + cb * Uextra + ch * RHS(U).  On the block-sparse kernel the update rides on the RHS pass (U's own rows are
+// in the box ring, Uextra is read by the lane that writes the same entries); every other kernel family evaluates the RHS
+// into scratch and combines in one pass (sbp_lincomb).
+static int32_t stage_fallback(sbp_ctx* ctx, double* Unext, const double* U, int64_t n, const double* Uextra, double ca,
+                              double cb, double ch, const double* rhs) {
+    return launch_lincomb(ctx, Unext, U, Uextra, rhs, n, ca, 0.0, Uextra ? cb : 0.0, ch);
+}
+static int32_t ensure_stage_buf(sbp_ctx* ctx, size_t doubles) {
+    if (ctx->stage_doubles >= doubles) return SBP_OK;
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stage_buf) cudaFree(ctx->stage_buf);
+    ctx->stage_buf = nullptr, ctx->stage_doubles = 0;
+    SBP_CUDA(cudaMalloc(&ctx->stage_buf, doubles * sizeof(double)));
+    ctx->stage_doubles = doubles;
+    return SBP_OK;
+}
+static bool stage_fusion_enabled() {
+    const char* e = getenv("SBP_FUSED_STAGE");  // 0: always RHS + sbp_lincomb (A/B measurements)
+    return !e || atoi(e) != 0;
+}
+
+int32_t sbp_rhs_advection2d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext, const double* U, int64_t B,
+                                  const double* g, int64_t g_stride, double ca, double cb, const double* Uextra,
+                                  double ch) {
+    int32_t rc = check_batch(ctx, op, Unext, U, B);
+    if (rc || B == 0) return rc;
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION2D, SBP_EINVAL, "not a 2D advection bundle");
+    SBP_REQUIRE(g != nullptr, SBP_EINVAL, "boundary data g is required");
+    SBP_REQUIRE(g_stride == 0 || g_stride >= op->N, SBP_EDIM, "g_stride must be 0 or >= N");
+    SBP_REQUIRE(Unext != U, SBP_EINVAL, "Unext must not alias U (other instances' rows of U are still being read)");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const sbp_op* A = op->inner;
+    const bool al = ((reinterpret_cast<uintptr_t>(Uextra) | reinterpret_cast<uintptr_t>(Unext)) & 15) == 0;
+    if (stage_fusion_enabled() && A->kind == SBP_OP_SPARSE && bsr_can_run(A, U) && al) {
+        const StageUpdate su{ca, cb, ch, Uextra};
+        return launch_bsr(ctx, A, Unext, U, B, -1.0, 0.0, op, g, g_stride, nullptr, &su);
+    }
+    const int64_t n = B * (int64_t)op->N;
+    rc = ensure_stage_buf(ctx, (size_t)n);
+    if (rc) return rc;
+    double* rhs = ctx->stage_buf;
+    rc = sbp_rhs_advection2d(ctx, op, rhs, U, B, g, g_stride, nullptr);
+    if (rc) return rc;
+    return stage_fallback(ctx, Unext, U, n, Uextra, ca, cb, ch, rhs);
+}
+
+int32_t sbp_rhs_advection1d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext, const double* U, int64_t B,
+                                  const double* bc, int64_t bc_stride, double ca, double cb, const double* Uextra,
+                                  double ch) {
+    int32_t rc = check_batch(ctx, op, Unext, U, B);
+    if (rc || B == 0) return rc;
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION1D, SBP_EINVAL, "not a 1D advection bundle");
+    SBP_REQUIRE(bc != nullptr, SBP_EINVAL, "boundary data bc is required");
+    SBP_REQUIRE(bc_stride == 0 || bc_stride >= 2, SBP_EDIM, "bc_stride must be 0 or >= 2");
+    SBP_REQUIRE(Unext != U, SBP_EINVAL, "Unext must not alias U (other instances' rows of U are still being read)");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const sbp_op* D = op->inner;
+    const bool al = ((reinterpret_cast<uintptr_t>(Uextra) | reinterpret_cast<uintptr_t>(Unext)) & 15) == 0;
+    if (stage_fusion_enabled() && D->kind == SBP_OP_SPARSE && bsr_can_run(D, U) && op->d_a == nullptr && al) {
+        Sat1D sat;
+        sat.bc = bc;
+        sat.bc_stride = bc_stride;
+        sat.a0 = op->sat_a0, sat.aN = op->sat_aN, sat.w0 = op->sat_w0, sat.wN = op->sat_wN;
+        sat.enabled = 1;
+        const StageUpdate su{ca, cb, ch, Uextra};
+        return launch_bsr(ctx, D, Unext, U, B, -1.0, 0.0, nullptr, nullptr, 0, &sat, &su);
+    }
+    const int64_t n = B * (int64_t)op->N;
+    rc = ensure_stage_buf(ctx, (size_t)n);
+    if (rc) return rc;
+    double* rhs = ctx->stage_buf;
+    rc = sbp_rhs_advection1d(ctx, op, rhs, U, B, bc, bc_stride, nullptr);
+    if (rc) return rc;
+    return stage_fallback(ctx, Unext, U, n, Uextra, ca, cb, ch, rhs);
 }
 
 int32_t sbp_axpbypcz(sbp_ctx* ctx, double* Y, const double* X, const double* Z, int64_t n, double a, double b,

@@ -68,7 +68,9 @@ constexpr int kBsrMaxStages = 4;
 // OUT: how results leave the SM.  0: 8-byte stores (dU not 16-byte aligned), 1: 16-byte stores, 2: staged in shared
 // memory and written by TMA tensor stores (beta == 0): asynchronous, so the output stream overlaps the next chunk's
 // tensor work instead of stalling every warp of the CTA on the store queue at the same time.
-template <int MTW, int MH, int SAT, int OUT>
+// FUSED: the Runge-Kutta stage update of sbp_rhs_advection*_stage rides on the RHS pass (separate instantiations, so that the
+// plain kernels keep their register allocation)
+template <int MTW, int MH, int SAT, int OUT, bool FUSED = false>
 __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
     k_bsr(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
@@ -274,6 +276,18 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
             if (mask & 1) gs0 = __ldg(p.g + n0);
             if (mask & 2) gs1 = __ldg(p.g + n1);
         }
+        // stage update: the lane's entries of `extra` are requested now and consumed after the chain
+        // (measured, N = 1296: 0.415 ms per stage with the loads ahead of the chain, 0.485 ms with the loads in the epilogue)
+        constexpr bool PREFETCH_EXTRA = FUSED;
+        double2 ex[PREFETCH_EXTRA ? MT : 1];
+        const bool with_extra = FUSED && p.cb != 0.0 && active && r0 < N;
+        if (PREFETCH_EXTRA && with_extra) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const int il = i0 + 8 * mt + g;
+                ex[mt] = *reinterpret_cast<const double2*>(p.extra + (long long)(b0 + (il < nb ? il : 0)) * N + r0);
+            }
+        }
         TR(1)  // tile/row/ring constants, boundary data
         mbar_wait(&bar_full[st], round & 1);
         TR(2)  // wait for the stage
@@ -393,7 +407,28 @@ __global__ void __launch_bounds__((kBsrGroups* kBsrCH* MH + 2) * 32)
                 }
             }
         }
-        TR(6)  // scale + SAT
+        if (FUSED && active && r0 < N) {
+            // Runge-Kutta stage update on the finished RHS: y <- ca * u + cb * extra + ch * y (u: own rows from the ring)
+            const int q0 = r0 / BX, q1 = (r0 + 1) / BX;
+            const int o0 = ring_off(((q0 - blo) << 8) | (r0 - q0 * BX));
+            const int o1 = ring_off(((q1 - blo) << 8) | (r0 + 1 - q1 * BX));
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                double2 e = make_double2(0.0, 0.0);
+                if (with_extra) {
+                    if (PREFETCH_EXTRA) {
+                        e = ex[PREFETCH_EXTRA ? mt : 0];
+                    } else {
+                        const int il = i0 + 8 * mt + g;
+                        e = *reinterpret_cast<const double2*>(p.extra + (long long)(b0 + (il < nb ? il : 0)) * N + r0);
+                    }
+                }
+                const double e0 = p.cb * e.x, e1 = p.cb * e.y;
+                acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, su[mt * MTS + o0], e0));
+                acc[mt][1] = fma(p.ch, acc[mt][1], fma(p.ca, su[mt * MTS + o1], e1));
+            }
+        }
+        TR(6)  // scale + SAT (+ stage update)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[st]);  // the stage (and the ring slots behind it) may be refilled
         TR(7)  // release
@@ -510,9 +545,9 @@ int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int b
     return SBP_OK;
 }
 
-template <int MTW, int MH, int SAT, int OUT>
+template <int MTW, int MH, int SAT, int OUT, bool FUSED = false>
 static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr<MTW, MH, SAT, OUT>;
+    auto kern = k_bsr<MTW, MH, SAT, OUT, FUSED>;
     constexpr int TI = 8 * MTW * MH;
     constexpr int THREADS = (kBsrGroups * kBsrCH * MH + 2) * 32;
     // the batch as a 2-D tensor [B][N] of doubles; input boxes = kBsrBX nodes x TI instances, output boxes = one quad
@@ -543,6 +578,13 @@ static int32_t launch_bsr_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int 
         case 1: return launch_bsr_k<MTW, MH, S, 1>(ctx, p, smem);            \
         default: return launch_bsr_k<MTW, MH, S, 0>(ctx, p, smem);           \
     }
+    if (p.fused) {  // stage updates: RHS kernels (2D or 1D SATs) with TMA output, one warp per row block
+        if constexpr (MH == 1) {
+            if (out == 2 && sat == 1) return launch_bsr_k<MTW, MH, 1, 2, true>(ctx, p, smem);
+            if (out == 2 && sat == 2) return launch_bsr_k<MTW, MH, 2, 2, true>(ctx, p, smem);
+        }
+        SBP_REQUIRE(false, SBP_EUNSUPPORTED, "fused stage update needs an RHS launch with TMA output");
+    }
     if (sat == 1) { SBP_BSR_OUT(1) }
     if (sat == 2) { SBP_BSR_OUT(2) }
     SBP_BSR_OUT(0)
@@ -554,7 +596,7 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
                          const Sat1D* sat);
 
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
-                   const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat) {
+                   const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat, const StageUpdate* su) {
     SBP_REQUIRE(B < (1ll << 31) - (1 << 20), SBP_EUNSUPPORTED, "block-sparse kernel: batch size must be < 2^31 - 2^20");
     BsrParams p;
     p.U = U;
@@ -576,6 +618,10 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.g = g;
     p.g_stride = g_stride;
     if (sat) p.sat = *sat;
+    if (su) {
+        SBP_REQUIRE((reinterpret_cast<uintptr_t>(su->extra) & 15) == 0, SBP_EUNSUPPORTED, "stage update: extra must be 16-byte aligned");
+        p.fused = 1, p.extra = su->extra, p.ca = su->ca, p.cb = su->extra ? su->cb : 0.0, p.ch = su->ch;
+    }
     const int satmode = (adv && adv->d_rb_bdiag) ? 1 : (sat && sat->enabled ? 2 : 0);
     // output path: TMA tensor stores when dU is 16-byte aligned and beta == 0 (SBP_BSR_OUT=1 forces plain stores)
     static int forced_out = -1;
@@ -591,14 +637,23 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
         if (B % 2) {
             const long long lastoff = (B - 1) * (long long)op->N;
             int32_t rc1;
+            double* out1 = dU + lastoff;
+            if (su) {  // stage update: RHS of the last instance into scratch (dU may alias su->extra), combined below
+                rc1 = ensure_scratch(ctx, (size_t)op->N);
+                if (rc1) return rc1;
+                out1 = ctx->scratch;
+            }
             if (sat && sat->enabled) {
                 Sat1D s1 = *sat;
                 s1.bc = sat->bc + (B - 1) * sat->bc_stride;
-                rc1 = launch_sparse_ex(ctx, op, dU + lastoff, U + lastoff, 1, alpha, beta, nullptr, nullptr, 0, nullptr, &s1);
+                rc1 = launch_sparse_ex(ctx, op, out1, U + lastoff, 1, alpha, beta, nullptr, nullptr, 0, nullptr, &s1);
             } else {
-                rc1 = launch_sparse(ctx, op, dU + lastoff, U + lastoff, 1, alpha, beta, adv,
+                rc1 = launch_sparse(ctx, op, out1, U + lastoff, 1, alpha, beta, adv,
                                     g ? g + (B - 1) * g_stride : nullptr, g_stride, nullptr);
             }
+            if (!rc1 && su)
+                rc1 = launch_lincomb(ctx, dU + lastoff, U + lastoff, su->extra ? su->extra + lastoff : nullptr, out1, op->N,
+                                     su->ca, 0.0, su->extra ? su->cb : 0.0, su->ch);
             if (rc1) return rc1;
             B -= 1;
             if (B == 0) return SBP_OK;
@@ -608,7 +663,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.B = B;
     {
         int32_t rc3 = SBP_OK;
-        if (launch_bsr3(ctx, op, p, satmode, vec, &rc3)) return rc3;  // lean consumer loop (bsr3.cu) when it applies
+        if (!su && launch_bsr3(ctx, op, p, satmode, vec, &rc3)) return rc3;  // lean consumer loop (bsr3.cu) when it applies
     }
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller

@@ -19,6 +19,11 @@ struct BsrParams {
     int Nh;                           // nodes per instance: N, or N/2 when a tensor row holds an instance PAIR (odd Nh)
     long long B;                      // tensor rows (instances, or instance pairs)
     double alpha, beta;
+    // fused Runge-Kutta stage update (sbp_rhs_advection*_stage): dU <- ca * U + cb * extra + ch * (RHS); U's own rows come from
+    // the ring, extra (may alias dU, not U) is read by the lane that writes the same entries
+    const double* __restrict__ extra = nullptr;
+    double ca = 0.0, cb = 0.0, ch = 1.0;
+    int fused = 0;
     int skew = 0;                     // bsr3.cu: start-up delay (cycles) of the second consumer warp of every scheduler
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
     const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows

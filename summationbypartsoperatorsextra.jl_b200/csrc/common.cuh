@@ -62,6 +62,8 @@ struct sbp_ctx {
     int64_t launches = 0;
     double* scratch = nullptr;  // per-CTA partial sums for deterministic batch reductions
     size_t scratch_doubles = 0;
+    double* stage_buf = nullptr;  // RHS of the un-fused stage updates (sbp_rhs_advection*_stage fallback)
+    size_t stage_doubles = 0;
     // host pipeline staging
     void* pipe_dev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][in/out]
     size_t pipe_bytes = 0;
@@ -179,8 +181,14 @@ bool bsr_can_run(const sbp_op* op, const double* U);
 struct BsrParams;
 // bsr3.cu: lean consumer loop (operator fragments prefetched from L2 into registers); false = not applicable, use k_bsr
 bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int out, int32_t* rc);
+// Runge-Kutta stage update fused into an RHS kernel: out <- ca * U + cb * extra + ch * RHS(U)  (extra may be null: cb ignored)
+struct StageUpdate {
+    double ca, cb, ch;
+    const double* extra;
+};
 int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha, double beta,
-                   const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat);
+                   const sbp_op* adv, const double* g, int64_t g_stride, const Sat1D* sat,
+                   const StageUpdate* su = nullptr);
 int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V, int64_t B,
                          int mode, double* out, double* out_sum);
 int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t B, double factor, int inverse);

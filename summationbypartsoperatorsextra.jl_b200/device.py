@@ -95,6 +95,34 @@ class Context:
             self.synchronize()
         return raw
 
+    def pci_bus_id(self) -> str:
+        buf = C.create_string_buffer(32)
+        check(self._lib.sbp_ctx_pci_bus_id(self.handle, buf, 32))
+        return buf.value.decode()
+
+    def bind_host_to_gpu_numa(self) -> list[int]:
+        """Pin the calling process to the CPUs of the GPU's NUMA node (sysfs `local_cpulist` of the device, intersected
+        with the current affinity mask) so that pinned buffers allocated afterwards and the copy-issuing thread are local
+        to the GPU's PCIe root.  Returns the CPU list in effect (unchanged when sysfs has no answer)."""
+        import os
+        cur = sorted(os.sched_getaffinity(0))
+        try:
+            with open(f"/sys/bus/pci/devices/{self.pci_bus_id()}/local_cpulist") as f:
+                txt = f.read().strip()
+            cpus = set()
+            for part in txt.split(","):
+                if not part:
+                    continue
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            want = sorted(cpus & set(cur))
+            if want and len(want) < len(cur):
+                os.sched_setaffinity(0, want)
+                return want
+        except (OSError, ValueError):
+            pass
+        return cur
+
     def pinned_empty(self, shape) -> np.ndarray:
         """Page-locked host array (for the end-to-end host-buffer path); release with `free_pinned`."""
         n = int(np.prod(shape))

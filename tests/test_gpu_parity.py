@@ -619,6 +619,63 @@ def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B, bsr_generation):
             assert rel_err(out[b], semio.rhs(U[b], 0.0)) <= TOL
 
 
+# ---- Runge-Kutta stage updates riding on the RHS pass (sbp_rhs_advection*_stage) ---------------------
+@pytest.mark.parametrize("n1,storage", [(12, "sparse"), (9, "sparse"), (12, "dense")])  # N = 144 even, 81 odd (pairs), dense fallback
+@pytest.mark.parametrize("B", [1, 2, 65, 1027])
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_stage_update_advection2d(ctx, n1, storage, B, fused, monkeypatch):
+    monkeypatch.setenv("SBP_FUSED_STAGE", fused)
+    D = _scattered_mfsbp(n1, seed=5)
+    a = (0.6, -1.0)
+    g = lambda x, t: np.cos(2 * x[0] - x[1] + t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, g, storage=storage)
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    U, E = rand_batch(B, D.N, 7), rand_batch(B, D.N, 8)
+    rhs = np.stack([semio.rhs(U[b], 0.2) for b in range(B)])
+    u, e, out = ctx.upload(U), ctx.upload(E), S.DeviceBatch.empty(ctx, B, D.N)
+    semi.stage(out, u, 0.2, 1.0, 0.037)                                  # u + h f(u)
+    assert rel_err(out.to_host(), U + 0.037 * rhs) <= TOL
+    semi.stage(out, u, 0.2, 0.644, 0.0243, 0.356, e)                      # a u + b e + h f(u)
+    assert rel_err(out.to_host(), 0.644 * U + 0.356 * E + 0.0243 * rhs) <= TOL
+    semi.stage(e, u, 0.2, 0.762, 0.0288, 0.238, e)                        # extra aliases the output
+    assert rel_err(e.to_host(), 0.762 * U + 0.238 * E + 0.0288 * rhs) <= TOL
+    G = rand_batch(B, D.N, 9)                                             # per-instance boundary data
+    semi.stage(out, u, 0.0, 0.5, -0.01, 0.25, ctx.upload(E), g=ctx.upload(G))
+    got = out.to_host()
+    for b in sorted({0, B // 2, B - 1}):
+        semio.bc = lambda node, t, b=b: G[b, int(np.argmin(np.sum((D.grid - node) ** 2, axis=1)))]
+        assert rel_err(got[b], 0.5 * U[b] + 0.25 * E[b] - 0.01 * semio.rhs(U[b], 0.0)) <= TOL
+    with pytest.raises(S.ArgumentError):
+        semi.stage(u, u, 0.2, 1.0, 0.1)
+
+
+@pytest.mark.parametrize("N,storage", [(101, "sparse"), (104, "sparse"), (64, "dense")])
+@pytest.mark.parametrize("B", [1, 3, 130, 1030])
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_stage_update_advection1d(ctx, N, storage, B, fused, monkeypatch):
+    monkeypatch.setenv("SBP_FUSED_STAGE", fused)
+    D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    D.storage = storage
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    for speed in (1.0, -0.7):
+        semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, lambda x: speed, False,
+                                                                       lambda t: 0.3 + t, lambda t: -0.2)
+        semio = O.AdvectionSemi1D(Do, lambda x: speed, lambda t: 0.3 + t, lambda t: -0.2)
+        U, E = rand_batch(B, N, 3), rand_batch(B, N, 4)
+        rhs = np.stack([semio.rhs(U[b], 0.1) for b in range(B)])
+        u, e, out = ctx.upload(U), ctx.upload(E), S.DeviceBatch.empty(ctx, B, N)
+        semi.stage(out, u, 0.1, 1.0, 0.009)
+        assert rel_err(out.to_host(), U + 0.009 * rhs) <= TOL
+        semi.stage(e, u, 0.1, 0.632, 0.0021, 0.368, e)
+        assert rel_err(e.to_host(), 0.632 * U + 0.368 * E + 0.0021 * rhs) <= TOL
+        BC = rand_batch(B, 2, 5)
+        semi.stage(out, u, 0.0, 0.4, 0.01, 0.6, ctx.upload(E), bc=ctx.upload(BC))
+        got = out.to_host()
+        for b in sorted({0, B // 2, B - 1}):
+            so = O.AdvectionSemi1D(Do, lambda x: speed, lambda t, b=b: BC[b, 0], lambda t, b=b: BC[b, 1])
+            assert rel_err(got[b], 0.4 * U[b] + 0.6 * E[b] + 0.01 * so.rhs(U[b], 0.0)) <= TOL
+
+
 # ---- operator container -> device -------------------------------------------------------------------
 def test_container_operator_on_device(ctx, tmp_path):
     D = _scattered_mfsbp(9, seed=4)
