@@ -203,6 +203,25 @@ function (semi::MultidimensionalLinearAdvectionNonperiodicSemidiscretization)(du
     return nothing
 end
 
+"""
+    stage!(unext, semi, u, t, ca, ch[, cb, extra])
+
+Runge-Kutta stage update riding on the RHS pass: `unext = ca*u + cb*extra + ch*semi(u, t)` in one kernel
+(`sbp_rhs_advection2d_stage`); `extra` may be `unext` itself, `unext` must not be `u`.  A fixed-step SSPRK53 step
+(examples/RBF_FSBP_advection.jl:45-51) is five such calls and never leaves the device.
+"""
+function stage!(unext::DeviceBatch, semi::MultidimensionalLinearAdvectionNonperiodicSemidiscretization, u::DeviceBatch, t,
+                ca::Real, ch::Real, cb::Real = 0.0, extra::Union{DeviceBatch, Nothing} = nothing)
+    op, _, mode = device_bundle(u.ctx, semi)
+    g = boundary_data(u.ctx, semi, mode, t)
+    check(ccall((:sbp_rhs_advection2d_stage, libsbp), Int32,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64,
+                 Ptr{Float64}, Float64),
+                u.ctx.handle, op.handle, unext.ptr, u.ptr, u.B, g.ptr, 0, Float64(ca), Float64(cb),
+                extra === nothing ? Ptr{Float64}(C_NULL) : extra.ptr, Float64(ch)))
+    return unext
+end
+
 function analyze_quantities(semi::MultidimensionalLinearAdvectionNonperiodicSemidiscretization, du::DeviceBatch,
                             u::DeviceBatch, p, t)
     op, _, mode = device_bundle(u.ctx, semi)
