@@ -264,7 +264,20 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
         r = bench(lambda i: semi(du, u, None, 0.1), B * N, 16.0, flops=2.0 * nnz * B)
         r["N"], r["nnz_per_row"], r["kernel"] = N, nnz / N, semi.device_op(ctx).info()["kernel"]
         out["config3_advection2d_rhs_sat"] = r
-        del U, Y
+        # one SSPRK53 step = 5 stage updates riding on the RHS pass (sbp_rhs_advection2d_stage): 2 without, 3 with the
+        # extra operand; algorithmic traffic 2 * 16 + 3 * 24 = 104 B/DOF per step
+        E = torch.rand((B, N), dtype=torch.float64, device=dev)
+        e = S.DeviceBatch.from_torch(ctx, E)
+        tab = semi.boundary_table(ctx, [0.1])
+        so = bench(lambda i: semi.stage(du, u, 0.1, 1.0, 1e-3, gptr=tab.ptr), B * N, 16.0)
+        se = bench(lambda i: semi.stage(du, u, 0.1, 0.6, 1e-3, 0.4, e, gptr=tab.ptr), B * N, 24.0)
+        step_ms = 2 * so["ms"] + 3 * se["ms"]
+        out["config3_ssprk53_step_fused_stage_updates"] = {
+            "ms_per_step": step_ms, "stage_ms": so["ms"], "stage_with_extra_operand_ms": se["ms"],
+            "gdof_steps_s": B * N / step_ms / 1e6, "hbm_gbs": 104.0 * B * N / step_ms / 1e6,
+            "hbm_frac": 104.0 * B * N / step_ms / 1e6 / hbm_peak, "kernel": "k_bsr<FUSED> (RHS + SAT + stage update)"}
+        tab.free()
+        del U, Y, E
     except Exception as e:  # pragma: no cover
         out["config3_advection2d_rhs_sat"] = {"error": str(e)[:200]}
     try:  # config 1 batched: banded 1D FD-SBP operator N = 101 (examples/RBF_FSBP_advection.jl sizes), RHS with SATs

@@ -47,7 +47,7 @@ def main():
         for _ in range(args.steps):
             S._lib.check(lib.sbp_apply_table(h, op.handle, C.c_void_p(du.ptr), C.c_void_p(u.ptr), B, None, 1.0, 0.0,
                                              C.c_void_p(e.ptr), C.c_void_p(e.ptr + 8 * B)))
-    elif args.workload == "config3":
+    elif args.workload in ("config3", "config3stage"):
         n1, B = 36, 1 << (args.batch_log2 or 16)
         D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, n1))
         nodes = D2.grid.copy()
@@ -68,8 +68,13 @@ def main():
             Dm, (1.0, 1.0), lambda x, t: float(np.exp(-30 * ((x[0] - t) ** 2 + (x[1] - t) ** 2))), storage="sparse")
         u = ctx.upload(rng.uniform(-1, 1, (B, Dm.N)))
         du = u.similar()
-        for _ in range(args.steps):
-            semi(du, u, None, 0.1)
+        if args.workload == "config3stage":  # Runge-Kutta stage update riding on the RHS pass, with the extra operand
+            e = u.copy()
+            for _ in range(args.steps):
+                semi.stage(du, u, 0.1, 0.6, 1e-3, 0.4, e)
+        else:
+            for _ in range(args.steps):
+                semi(du, u, None, 0.1)
     elif args.workload == "config5":
         N, B = 4096, 1 << (args.batch_log2 or 12)
         Sk = rng.normal(size=(N, N))
