@@ -27,11 +27,14 @@
 #include "bsr.cuh"
 
 // -DSBP_B3_EXP=n: what-if builds for bottleneck hunting (WRONG RESULTS): 1 = no DMMA, 2 = no A-operand loads inside the chain,
-// 3 = no TMA box loads, 4 = no output, 5 = all tiles store to the rows of tile 0, 6 = all tiles load the rows of tile 0
+// 3 = no TMA box loads, 4 = no output, 5 = all tiles store to the rows of tile 0, 6 = all tiles load the rows of tile 0, 10 = no proxy fence before the TMA stores
 // (7 = staging + fence but no TMA store, 8 = TMA stores without staging/fence, 9 = accumulators consumed + fence, no stores:
 // measured in session 4, code removed)
 #ifndef SBP_B3_EXP
 #define SBP_B3_EXP 0
+#endif
+#ifndef SBP_B3_PING
+#define SBP_B3_PING 0  // 1: the two consumer warps of a scheduler take turns on the tensor pipe (token through named barriers)
 #endif
 #ifndef SBP_B3_DEFER
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
@@ -235,6 +238,10 @@ __global__ void __launch_bounds__((CW + 2) * 32)
     sgn = pin(sgn);
     uint32_t svst = sval32, spst = spos32;  // fragment buffers of stage st
 
+    // PING: tensor-pipe token of this warp's scheduler, barrier id (1 + 2 * scheduler + k) = "warp k may multiply"
+    constexpr bool PING = SBP_B3_PING && CW == kBsrCH;
+    const int pp_me = 1 + 2 * (warp & 3) + (warp >> 2), pp_next = 1 + 2 * (warp & 3) + (1 - (warp >> 2));
+    if (PING && (warp >> 2) == 1) named_bar_arrive(pp_next, 64);  // the first turn belongs to warp k = 0
     if (p.skew > 0 && warp >= 4) {  // de-phase the two consumer warps of a scheduler (chains against scalar phases)
         const long long t0 = clock64();
         while (clock64() - t0 < p.skew) {
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__((CW + 2) * 32)
         }
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(a[mt][0], a[mt][1]);
-        fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+        if (SBP_B3_EXP != 10) fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy); what-if 10: none
         __syncwarp();
         if (lane == 0) {
             const int yo = SBP_B3_EXP == 5 ? 0 : yb0;  // what-if 5: every tile writes the rows of tile 0 (L2-resident output)
@@ -300,6 +307,7 @@ __global__ void __launch_bounds__((CW + 2) * 32)
 
         mbar_wait(&fbar_full[fst], fphase);
         mbar_wait(&bar_full[st], phase);
+        if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
         // ---- DMMA chain, two fragments per trip: operands one fragment ahead, ring codes two ahead ----
         if (active && nf > 0) {
             // byte code -> shared address of the lane's A operand (m-tile 0): add the window base, wrap, add the lane's row
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__((CW + 2) * 32)
         }
 
         const int nb = min(Bir - b0, TI);
+        if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the other warp of this scheduler may start
         // blocks that carry SAT terms finish their accumulators now (the terms read the ring); for the others a deferred
         // epilogue also takes over the scaling by alpha
         const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
@@ -490,6 +499,7 @@ __global__ void __launch_bounds__((CW + 2) * 32)
      }
     }
 done:
+    if (PING && (warp >> 2) == 0) named_bar_sync(pp_me, 64);  // absorb the last token
     if (DEFER && (pv_state & 1)) {  // the last block of this warp
         if (pv_state & 4) emit(accs[DEFER ? 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
         else emit(accs[0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
