@@ -553,6 +553,52 @@ def test_config2_full_size_properties(ctx):
     assert np.max(np.abs(e[:R] - eref) / eref) <= TOL and abs(etot - eref.sum() * (B // R)) <= 1e-12 * etot
 
 
+def test_config3_full_size_properties(ctx):
+    """BASELINE config 3 at full size (2D cloud N = 36^2 = 1296, B = 65536, RHS with SAT on the block-sparse kernel):
+    instances are tiled copies of 512 distinct vectors => the result is the same tiling bitwise, the first block matches
+    the oracle, and the fused SSPRK53-type stage update of the same batch equals ca*u + cb*e + ch*rhs."""
+    B, R = 65536, 512
+    D = _scattered_mfsbp(36, seed=0)
+    a = (1.0, 1.0)
+    g = lambda x, t: np.exp(-30 * ((x[0] - t) ** 2 + (x[1] - t) ** 2))
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, g, storage="sparse")
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    base = rand_batch(R, D.N, 21)
+    u = ctx.upload(np.tile(base, (B // R, 1)))
+    du = S.DeviceBatch.empty(ctx, B, D.N)
+    semi(du, u, None, 0.15)
+    assert semi.device_op(ctx).info()["kernel"] == "bsr_dmma"
+    out = du.to_host().reshape(B // R, R, D.N)
+    ref = np.stack([semio.rhs(base[b], 0.15) for b in range(R)])
+    assert rel_err(out[0], ref) <= TOL
+    assert all(np.array_equal(out[0], out[k]) for k in range(1, B // R))
+    e = ctx.upload(np.tile(rand_batch(R, D.N, 22), (B // R, 1)))
+    ehost = e.to_host()[:R]
+    semi.stage(e, u, 0.15, 0.644, 0.0243, 0.356, e)
+    got = e.to_host().reshape(B // R, R, D.N)
+    assert rel_err(got[0], 0.644 * base + 0.356 * ehost + 0.0243 * ref) <= TOL
+    assert all(np.array_equal(got[0], got[k]) for k in range(1, B // R))
+
+
+def test_config4_full_size_properties(ctx):
+    """BASELINE config 4 at full size (sub-cell table N = 16, G = 8, B = 2^22, fused energy): tiled batch => tiled result
+    bitwise (the tiling period is a multiple of G), first block and energies against the oracle, global energy sum."""
+    B, R = 1 << 22, 4096
+    ops, ops_o = _subcell_table()
+    table = S.OperatorTable(ops)
+    base = rand_batch(R, 16, 23)
+    u = ctx.upload(np.tile(base, (B // R, 1)))
+    du = S.DeviceBatch.empty(ctx, B, 16)
+    _, E, Esum = table.mul_(du, u, energy=True, energy_sum=True)
+    out = du.to_host().reshape(B // R, R, 16)
+    ref = np.stack([ops_o[b % 8].mul(base[b]) for b in range(R)])
+    eref = np.array([ops_o[b % 8].integrate(np.square, base[b]) for b in range(R)])
+    assert rel_err(out[0], ref) <= TOL
+    assert all(np.array_equal(out[0], out[k]) for k in range(1, B // R, 37))
+    assert np.max(np.abs(E[:R] - eref) / eref) <= TOL
+    assert abs(Esum - eref.sum() * (B // R)) <= 1e-12 * Esum
+
+
 def test_config5_sized_dense_gemm_checksum(ctx):
     """config 5 shape at reduced batch (N = 4096 dense, B = 2048): column-checksum identity
     sum_i w_i (D u)_i = (D' w)' u  for every instance."""
