@@ -75,8 +75,10 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 // CW consumer warps (8 or 12) share the row blocks of the item stream round-robin: block k = 8 * item + slot belongs to warp
 // k % CW.  CW = 8: a warp keeps its slot and has a block in every item; CW = 12: three consumer warps per scheduler, a warp
 // has a block in two out of three items (it still passes every item's "full" barrier, in order).
-template <int MT, int SAT, int OUT, int CW>
-__global__ void __launch_bounds__((CW + 2) * 32)
+// HELP: four extra warps issue the TMA stores (helper h serves consumer warps h and h + 4): a consumer warp deposits its
+// accumulators in its staging buffer and signals an mbarrier instead of issuing the stores and waiting for the buffer itself.
+template <int MT, int SAT, int OUT, int CW, bool HELP = false>
+__global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
@@ -91,6 +93,8 @@ __global__ void __launch_bounds__((CW + 2) * 32)
     // boxes and operator fragments have separate stage counts: p.nst box stages (HBM latency: as deep as the ring allows),
     // kB3FragStages fragment stages (L2 latency: two are enough, each costs maxf * 272 bytes)
     __shared__ uint64_t bar_full[kB3Stages], bar_empty[kB3Stages], fbar_full[kB3FragStages], fbar_empty[kB3FragStages];
+    __shared__ uint64_t out_full[kBsrCH], out_empty[kBsrCH];  // HELP: staging buffer of consumer warp w filled / stored
+    static_assert(!HELP || (CW == kBsrCH && OUT == 2), "helper warps: 8 consumer warps with TMA output");
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
     int* s_pos = reinterpret_cast<int*>(s_val + (size_t)kB3FragStages * p.maxf * 32);  // kB3FragStages * maxf * PS
@@ -110,10 +114,55 @@ __global__ void __launch_bounds__((CW + 2) * 32)
             mbar_init(&fbar_full[s], 1);
             mbar_init(&fbar_empty[s], CONS);
         }
+        for (int s = 0; s < kBsrCH; s++) {
+            mbar_init(&out_full[s], 1);
+            mbar_init(&out_empty[s], 1);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
+    if (HELP && warp >= CONS + 2) {
+        // ------- store helpers: per item and served consumer warp, wait for its staging buffer, store the two quads, hand it back -------
+        if (lane == 0) {
+            const int h = warp - (CONS + 2);
+            int c = 0, ph = 0;
+            const int4* rec = p.item;
+            int rowA[2], rowB[2];
+            for (int k = 0; k < 2; k++) {
+                const int4 a = __ldg(rec + 2 * (h + 4 * k));
+                rowA[k] = a.z, rowB[k] = a.w;
+            }
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b0 = (int)(tile * TI);
+                for (int cc = 0; cc < p.nch; cc++) {
+                    const int cn = c + 1 < p.nch ? c + 1 : 0;
+                    int nA[2], nB[2];
+                    for (int k = 0; k < 2; k++) {  // next item's rows (the records repeat with the tile)
+                        const int4 a = __ldg(rec + 2 * (kBsrCH * cn + h + 4 * k));
+                        nA[k] = a.z, nB[k] = a.w;
+                    }
+                    for (int k = 0; k < 2; k++) {
+                        const int w = h + 4 * k;
+                        mbar_wait(&out_full[w], ph);
+                        const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
+                        if (rowA[k] < N) {
+                            tma_store_2d(&tmap_out, rowA[k], b0, so);
+                            if (rowB[k] < N) tma_store_2d(&tmap_out, rowB[k], b0, so + 8 * MT * 4);
+                            bulk_commit();
+                            bulk_wait_read<0>();
+                        }
+                        mbar_arrive(&out_empty[w]);
+                    }
+                    for (int k = 0; k < 2; k++) rowA[k] = nA[k], rowB[k] = nB[k];
+                    c = cn;
+                    ph ^= 1;
+                }
+            }
+            bulk_wait<0>();
+        }
+        return;
+    }
     if (warp >= CONS) {
         // ------- producers (as in bsr.cu): warp CONS requests the boxes of the batch, warp CONS + 1 the operator fragments -------
         if (lane == 0) {
@@ -250,7 +299,8 @@ __global__ void __launch_bounds__((CW + 2) * 32)
     // DEFER: the results of a block leave the registers one block later, after the NEXT chain has been issued (two accumulator
     // sets, the loop is unrolled by two for static register indices): the warp never waits for its own DMMAs to complete, and
     // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
-    constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0;
+    constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0 && !HELP;
+    int out_phase = 0;
     double accs[DEFER ? 2 : 1][MT][2];
     int pv_rowA = 0, pv_rowB = 0, pv_b0 = 0, pv_state = 0;  // deferred block: rows of its quads, first tensor row, 1 = pending | 2 = scale | 4 = set
     // staging + TMA stores of one block's accumulators
@@ -443,6 +493,17 @@ __global__ void __launch_bounds__((CW + 2) * 32)
             if (pv_state & 1) emit(accs[DEFER ? hf ^ 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
             pv_rowA = r0.a.z, pv_rowB = r0.a.w, pv_b0 = b0;
             pv_state = (active ? 1 : 0) | (scale_later ? 2 : 0) | (hf ? 4 : 0);
+        } else if (HELP) {
+            // ---- results to the warp's staging buffer; a helper warp stores them (every item signals, active or not) ----
+            mbar_wait(&out_empty[warp], out_phase ^ 1);  // the helper has stored the previous contents (first item: passes)
+            out_phase ^= 1;
+            if (active) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
+                fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&out_full[warp]);
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
             //      one lane stores quad A and quad B as {4 rows x 8*MT instances} boxes ----
@@ -504,24 +565,24 @@ done:
         if (pv_state & 4) emit(accs[DEFER ? 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
         else emit(accs[0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
     }
-    if (OUT == 2 && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
+    if (OUT == 2 && !HELP && lane == 0) bulk_wait<0>();  // all output boxes of this warp have been written
 }
 
 static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out, int cw) {
     const size_t ops = ((size_t)kB3FragStages * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
     // staging per consumer warp (TMA tensor stores only): 2 quads x instances x 4 rows
-    const size_t staging = out == 2 ? (size_t)cw * 2 * 8 * MT * 4 * 8 : 0;
+    const size_t staging = out == 2 ? (size_t)(cw == 12 ? 12 : 8) * 2 * 8 * MT * 4 * 8 : 0;
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
 static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int out, int cw) {
     return bsr3_smem(op, MT, D, out, cw) + 1024 <= (size_t)ctx->smem_optin;
 }
 
-template <int MT, int SAT, int OUT, int CW>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false>
 static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr3<MT, SAT, OUT, CW>;
+    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP>;
     constexpr int TI = 8 * MT;
-    constexpr int THREADS = (CW + 2) * 32;
+    constexpr int THREADS = (CW + 2 + (HELP ? 4 : 0)) * 32;
     CUtensorMap tmap, tmap_out;
     int32_t rc = make_tmap(&tmap, p.U, p.N, p.B, kBsrBX, TI);
     if (rc) return rc;
@@ -540,7 +601,9 @@ template <int MT>
 static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int sat, int out, int cw) {
 #define SBP_BSR3_OUT(S)                                                                                    \
     switch (out) {                                                                                         \
-        case 2: return cw == 12 ? launch_bsr3_k<MT, S, 2, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 2, 8>(ctx, p, smem); \
+        case 2: return cw == 12 ? launch_bsr3_k<MT, S, 2, 12>(ctx, p, smem)                                \
+                          : cw == 9 ? launch_bsr3_k<MT, S, 2, 8, true>(ctx, p, smem)                       \
+                                    : launch_bsr3_k<MT, S, 2, 8>(ctx, p, smem);                            \
         case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, 8>(ctx, p, smem); \
         default: return launch_bsr3_k<MT, S, 0, 8>(ctx, p, smem);                                          \
     }
@@ -560,15 +623,26 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
         e = getenv("SBP_BSR_DEPTH");
         forced_d = e ? atoi(e) : 99;
     }
+    // Default rule (measured, profiles/r1k_bsr3_notes.txt section 5): with the store-helper warps this kernel beats k_bsr on
+    // every RHS launch (2D or 1D SATs fused) and on instance-pair views (odd N), by 2-18 %; k_bsr stays ahead on plain
+    // even-N applies.  SBP_BSR_V3 (read at every launch: the tests switch it): unset = that rule, 0 = always k_bsr,
+    // 1 = this kernel for every large batch, 2 = always this kernel.
     const char* ev = getenv("SBP_BSR_V3");
-    const int enabled = ev ? atoi(ev) : 0;  // measured (profiles/r1k_bsr3_notes.txt): no faster than k_bsr -> opt-in
+    const int enabled = ev ? atoi(ev) : -1;
     if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
+    if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N))) return false;
     static int forced_cw = -1;
     if (forced_cw < 0) {
         const char* e = getenv("SBP_BSR_CW");
         forced_cw = e ? atoi(e) : 8;
     }
-    const int cw = (forced_cw == 12 && out != 0) ? 12 : 8;
+    static int help = -1;
+    if (help < 0) {
+        const char* e = getenv("SBP_BSR_HELP");
+        help = e ? atoi(e) : 1;
+    }
+    // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
+    const int cw = (forced_cw == 12 && out != 0) ? 12 : (help && out == 2) ? 9 : 8;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;
@@ -576,7 +650,7 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     while (MT > 4 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) MT--;
     if (forced_mt >= 4 && forced_mt <= 8) MT = forced_mt;
     if (!bsr3_fits(ctx, op, MT, 1, out, cw)) return false;
-    if (enabled != 2 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count / 2) return false;  // small batches: smaller tiles of k_bsr
+    if (enabled != 2 && (B + 8 * MT - 1) / (8 * MT) < ctx->sm_count) return false;  // small batches: smaller tiles of k_bsr
     int D = 1;
     for (int d = 2; d < kB3Stages; d++)
         if (d <= forced_d && bsr3_fits(ctx, op, MT, d, out, cw)) D = d;
