@@ -663,7 +663,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.B = B;
     {
         int32_t rc3 = SBP_OK;
-        if (!su && launch_bsr3(ctx, op, p, satmode, vec, &rc3)) return rc3;  // lean consumer loop (bsr3.cu) when it applies
+        if (launch_bsr3(ctx, op, p, satmode, vec, &rc3)) return rc3;  // lean consumer loop (bsr3.cu) when it applies
     }
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller

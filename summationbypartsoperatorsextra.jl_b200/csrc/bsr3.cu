@@ -77,7 +77,8 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 // has a block in two out of three items (it still passes every item's "full" barrier, in order).
 // HELP: four extra warps issue the TMA stores (helper h serves consumer warps h and h + 4): a consumer warp deposits its
 // accumulators in its staging buffer and signals an mbarrier instead of issuing the stores and waiting for the buffer itself.
-template <int MT, int SAT, int OUT, int CW, bool HELP = false>
+// FUSED: Runge-Kutta stage update on the finished RHS (sbp_rhs_advection*_stage), as in k_bsr<..., FUSED>.
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
 __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
@@ -351,6 +352,17 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         double(&acc)[MT][2] = accs[DEFER ? hf : 0];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
+        // stage update: the lane's entries of `extra` are requested now and consumed after the chain
+        double2 ex[FUSED ? MT : 1];
+        const bool with_extra = FUSED && p.cb != 0.0 && active && r0w < Nr;
+        if (FUSED && with_extra) {
+            const int nbx = min(Bir - b0, TI);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const int il = 8 * mt + g;
+                ex[FUSED ? mt : 0] = *reinterpret_cast<const double2*>(p.extra + (long long)(b0 + (il < nbx ? il : 0)) * N + r0w);
+            }
+        }
         // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
         uint32_t sv = svst + (uint32_t)r0.a.x * 256u, sp = spst + (uint32_t)r0.a.x * (4u * PS);
         const uint32_t spl = sp + (uint32_t)(nf - 1) * (4u * PS);  // last code of the block (look-ahead loads are clamped to it)
@@ -480,6 +492,17 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     }
                 }
             }
+            if (FUSED && r0w < Nr) {  // y <- ca * u + cb * extra + ch * y (u: the lane's own rows from the ring)
+                const uint32_t o0 = ring_elem(r0w), o1 = ring_elem(r0w + 1);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const double2 e = with_extra ? ex[FUSED ? mt : 0] : make_double2(0.0, 0.0);
+                    const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
+                    const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
+                    acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
+                    acc[mt][1] = fma(p.ch, acc[mt][1], fma(p.ca, u1, p.cb * e.y));
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) {
@@ -578,9 +601,9 @@ static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int o
     return bsr3_smem(op, MT, D, out, cw) + 1024 <= (size_t)ctx->smem_optin;
 }
 
-template <int MT, int SAT, int OUT, int CW, bool HELP = false>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
 static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP>;
+    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP, FUSED>;
     constexpr int TI = 8 * MT;
     constexpr int THREADS = (CW + 2 + (HELP ? 4 : 0)) * 32;
     CUtensorMap tmap, tmap_out;
@@ -606,6 +629,10 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
                                     : launch_bsr3_k<MT, S, 2, 8>(ctx, p, smem);                            \
         case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, 8>(ctx, p, smem); \
         default: return launch_bsr3_k<MT, S, 0, 8>(ctx, p, smem);                                          \
+    }
+    if (p.fused) {  // stage updates: RHS launches with TMA output and store helpers (checked by launch_bsr3)
+        if (sat == 1) return launch_bsr3_k<MT, 1, 2, 8, true, true>(ctx, p, smem);
+        return launch_bsr3_k<MT, 2, 2, 8, true, true>(ctx, p, smem);
     }
     if (sat == 1) { SBP_BSR3_OUT(1) }
     if (sat == 2) { SBP_BSR3_OUT(2) }
@@ -642,7 +669,11 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
         help = e ? atoi(e) : 1;
     }
     // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
-    const int cw = (forced_cw == 12 && out != 0) ? 12 : (help && out == 2) ? 9 : 8;
+    const int cw = (forced_cw == 12 && out != 0 && !p.fused) ? 12 : (help && out == 2) ? 9 : 8;
+    // fused stage updates: helper variant of an RHS launch, and only without the extra operand (measured, N = 1296: stage
+    // 0.287 vs 0.303 ms on k_bsr without it, but 0.527 vs 0.414 ms with it: 128 registers per thread are too few for the
+    // prefetched operand)
+    if (p.fused && (cw != 9 || satmode == 0 || p.cb != 0.0)) return false;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;

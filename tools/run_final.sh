@@ -1,7 +1,7 @@
 set -x
-timeout -s KILL 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1l.log 2>&1; tail -2 gpurun_out/pytest_gpu_r1l.log
+timeout -s KILL 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1n.log 2>&1; tail -2 gpurun_out/pytest_gpu_r1n.log
 timeout -s KILL 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout -s KILL 600 python bench.py > gpurun_out/bench_r1l.log 2> gpurun_out/bench_r1l.err; tail -c 400 gpurun_out/bench_r1l.log; tail -3 gpurun_out/bench_r1l.err
-timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_bench_r1l.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_bench_r1l.log 2>&1; tail -1 gpurun_out/ncu_bench_r1l.log | cut -c1-120
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:k_bsr -c 1 -s 2 -o gpurun_out/prof_config3stage_r1l -f python tools/prof_run.py --workload config3stage --steps 4 > gpurun_out/ncu_c3stage_r1l.log 2>&1; tail -1 gpurun_out/ncu_c3stage_r1l.log
-timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:k_bsr -c 1 -s 2 -o gpurun_out/prof_config3_r1l -f python tools/prof_run.py --workload config3 --steps 4 > gpurun_out/ncu_c3_r1l.log 2>&1; tail -1 gpurun_out/ncu_c3_r1l.log
+timeout -s KILL 600 python bench.py > gpurun_out/bench_r1n.log 2> gpurun_out/bench_r1n.err; tail -c 400 gpurun_out/bench_r1n.log; tail -3 gpurun_out/bench_r1n.err
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_bench_r1n.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_bench_r1n.log 2>&1; tail -1 gpurun_out/ncu_bench_r1n.log | cut -c1-120
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:k_bsr -c 1 -s 2 -o gpurun_out/prof_config3stage_r1n -f python tools/prof_run.py --workload config3stage --steps 4 > gpurun_out/ncu_c3stage_r1n.log 2>&1; tail -1 gpurun_out/ncu_c3stage_r1n.log
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:k_bsr -c 1 -s 2 -o gpurun_out/prof_config3_r1n -f python tools/prof_run.py --workload config3 --steps 4 > gpurun_out/ncu_c3_r1n.log 2>&1; tail -1 gpurun_out/ncu_c3_r1n.log
