@@ -1,4 +1,5 @@
-// bsr3.cu -- K2'/K3', experimental second generation of the block-sparse DMMA kernel (bsr.cu); OPT-IN (SBP_BSR_V3=1|2).
+// bsr3.cu -- K2'/K3', second generation of the block-sparse DMMA kernel (bsr.cu): default for RHS launches and odd-N pair
+// views (launch_bsr3 below; SBP_BSR_V3=0 switches it off), k_bsr keeps the plain even-N applies and the small batches.
 // Same operator image, data movement (TMA box ring, operator fragments per chunk by bulk copy, TMA tensor stores) and
 // barrier protocol as k_bsr, with a leaner consumer loop and the tooling used to find out what bounds the kernel.
 //
@@ -15,8 +16,10 @@
 //  * box stages and operator-fragment stages are decoupled (p.nst box stages, two fragment stages): with plain 16-byte
 //    stores (no staging buffers) the ring of config 3 holds two chunks of lookahead at 56 instances per tile;
 //  * -DSBP_B3_EXP=n what-if builds and SBP_BSR_SKEW (start-up delay of every second consumer warp).
-// Result (profiles/r1k_bsr3_notes.txt): 14 % fewer warp instructions, 15 % less time outside the DMMA chain -- and the
-// same 0.326-0.330 ms on BASELINE config 3 as k_bsr (banded 1D operators: slower).  The what-if builds show why: without
+//  * four store-helper warps (HELP) take the staging buffers from the consumer warps through mbarriers and issue the TMA
+//    stores: the consumer warps neither issue stores nor wait for their buffers (config 3: 0.3256 -> 0.311 ms);
+// Result (profiles/r1k_bsr3_notes.txt): 14 % fewer warp instructions, 15 % less time outside the DMMA chain -- and, before
+// the helper warps, the same 0.326-0.330 ms on BASELINE config 3 as k_bsr.  The what-if builds show why: without
 // DMMAs 0.252 ms, without output 0.166 ms (= the tensor pipe: 2 warps x 64 DMMA x 16 cycles per scheduler and chunk),
 // full kernel 0.330 ms = pipe time + the non-chain time of a warp: the two consumer warps of a scheduler run their
 // chains at the same time and their scalar phases at the same time, whatever the pipeline depth, the start-up skew or
