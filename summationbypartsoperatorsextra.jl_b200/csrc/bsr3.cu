@@ -370,21 +370,29 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         uint32_t sv = svst + (uint32_t)r0.a.x * 256u, sp = spst + (uint32_t)r0.a.x * (4u * PS);
         const uint32_t spl = sp + (uint32_t)(nf - 1) * (4u * PS);  // last code of the block (look-ahead loads are clamped to it)
 
+        // byte code -> shared address of the lane's A operand (m-tile 0): add the window base, wrap, add the lane's row
+        auto conv = [&](uint32_t q) {
+            const uint32_t v = q + baseB;
+            return su32 + min(v, v - ringBr);  // v < 2 ringB: subtracts ringB iff v >= ringB (unsigned wrap otherwise)
+        };
+        auto flip = [&](double v) { return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v)); };
+        const bool work = active && nf > 0;
+        // the operator fragments arrive ahead of the boxes: the first B operand and the ring addresses of the first two
+        // fragments are fetched before the wait for the boxes
         mbar_wait(&fbar_full[fst], fphase);
+        double b0v = 0.0;
+        uint32_t adr0 = su32, adr = su32;
+        if (work) {
+            b0v = flip(lds64<0>(sv));
+            adr0 = conv(lds32<0>(sp));
+            adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
+        }
         mbar_wait(&bar_full[st], phase);
         if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
         // ---- DMMA chain, two fragments per trip: operands one fragment ahead, ring codes two ahead ----
-        if (active && nf > 0) {
-            // byte code -> shared address of the lane's A operand (m-tile 0): add the window base, wrap, add the lane's row
-            auto conv = [&](uint32_t q) {
-                const uint32_t v = q + baseB;
-                return su32 + min(v, v - ringBr);  // v < 2 ringB: subtracts ringB iff v >= ringB (unsigned wrap otherwise)
-            };
-            auto flip = [&](double v) { return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v)); };
+        if (work) {
             double a0[MT], a1[MT];
-            double b0v = flip(lds64<0>(sv));
-            lds_tiles<MT, MTB>(a0, conv(lds32<0>(sp)));
-            uint32_t adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
+            lds_tiles<MT, MTB>(a0, adr0);
             int rem = nf;
             while (rem >= 2) {
 #if SBP_B3_EXP != 2
