@@ -83,7 +83,8 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 // FUSED: Runge-Kutta stage update on the finished RHS (sbp_rhs_advection*_stage), as in k_bsr<..., FUSED>.
 template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
 __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
-    k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out) {
+    k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
+           const __grid_constant__ CUtensorMap tmap_ex) {
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
     constexpr int TI = 8 * MT;
@@ -98,6 +99,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // kB3FragStages fragment stages (L2 latency: two are enough, each costs maxf * 272 bytes)
     __shared__ uint64_t bar_full[kB3Stages], bar_empty[kB3Stages], fbar_full[kB3FragStages], fbar_empty[kB3FragStages];
     __shared__ uint64_t out_full[kBsrCH], out_empty[kBsrCH];  // HELP: staging buffer of consumer warp w filled / stored
+    __shared__ uint64_t ext_full[kBsrCH];  // HELP + FUSED: the quads of `extra` for the warp's next block are in its staging buffer
+    // XT: the extra operand of a fused stage update travels through the staging buffers (TMA loads issued by the helpers)
+    const bool XT = HELP && FUSED && p.cb != 0.0;
     static_assert(!HELP || (CW == kBsrCH && OUT == 2), "helper warps: 8 consumer warps with TMA output");
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
@@ -121,6 +125,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         for (int s = 0; s < kBsrCH; s++) {
             mbar_init(&out_full[s], 1);
             mbar_init(&out_empty[s], 1);
+            mbar_init(&ext_full[s], 1);
         }
         mbar_fence_init();
     }
@@ -137,6 +142,16 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 const int4 a = __ldg(rec + 2 * (h + 4 * k));
                 rowA[k] = a.z, rowB[k] = a.w;
             }
+            // XT: quads rA / rB of `extra` for tensor rows y.. of consumer warp w -> its staging buffer, completion on ext_full[w]
+            auto load_extra = [&](int w, int rA, int rB, int y) {
+                double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
+                const unsigned quads = (rA < N ? 1u : 0u) + (rA < N && rB < N ? 1u : 0u);
+                mbar_arrive_expect_tx(&ext_full[w], quads * (unsigned)(4 * TI * 8));
+                if (rA < N) tma_load_2d(so, &tmap_ex, rA, y, &ext_full[w]);
+                if (rA < N && rB < N) tma_load_2d(so + 8 * MT * 4, &tmap_ex, rB, y, &ext_full[w]);
+            };
+            if (XT && (long long)blockIdx.x < ntiles)
+                for (int k = 0; k < 2; k++) load_extra(h + 4 * k, rowA[k], rowB[k], (int)(blockIdx.x * TI));
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
                 for (int cc = 0; cc < p.nch; cc++) {
@@ -146,6 +161,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         const int4 a = __ldg(rec + 2 * (kBsrCH * cn + h + 4 * k));
                         nA[k] = a.z, nB[k] = a.w;
                     }
+                    // first tensor row of the next item (same tile, or this CTA's next tile); -1: there is none
+                    const long long ntile = cc + 1 < p.nch ? tile : tile + gridDim.x;
+                    const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
                     for (int k = 0; k < 2; k++) {
                         const int w = h + 4 * k;
                         mbar_wait(&out_full[w], ph);
@@ -156,6 +174,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                             bulk_commit();
                             bulk_wait_read<0>();
                         }
+                        if (XT && nb0 >= 0) load_extra(w, nA[k], nB[k], nb0);  // the buffer is free: fetch the next block's operand
                         mbar_arrive(&out_empty[w]);
                     }
                     for (int k = 0; k < 2; k++) rowA[k] = nA[k], rowB[k] = nB[k];
@@ -304,7 +323,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // sets, the loop is unrolled by two for static register indices): the warp never waits for its own DMMAs to complete, and
     // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
     constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0 && !HELP;
-    int out_phase = 0;
+    int out_phase = 0, ext_phase = 0;
     double accs[DEFER ? 2 : 1][MT][2];
     int pv_rowA = 0, pv_rowB = 0, pv_b0 = 0, pv_state = 0;  // deferred block: rows of its quads, first tensor row, 1 = pending | 2 = scale | 4 = set
     // staging + TMA stores of one block's accumulators
@@ -356,14 +375,14 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
         // stage update: the lane's entries of `extra` are requested now and consumed after the chain
-        double2 ex[FUSED ? MT : 1];
+        double2 ex[(FUSED && !HELP) ? MT : 1];  // (with helper warps the operand comes through the staging buffer: XT)
         const bool with_extra = FUSED && p.cb != 0.0 && active && r0w < Nr;
-        if (FUSED && with_extra) {
+        if (FUSED && !HELP && with_extra) {
             const int nbx = min(Bir - b0, TI);
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 const int il = 8 * mt + g;
-                ex[FUSED ? mt : 0] = *reinterpret_cast<const double2*>(p.extra + (long long)(b0 + (il < nbx ? il : 0)) * N + r0w);
+                ex[(FUSED && !HELP) ? mt : 0] = *reinterpret_cast<const double2*>(p.extra + (long long)(b0 + (il < nbx ? il : 0)) * N + r0w);
             }
         }
         // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
@@ -428,6 +447,10 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // epilogue also takes over the scaling by alpha
         const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
         const bool scale_later = DEFER && scale_needed && !sat_block;
+        if (XT) {  // the helper has put this block's quads of `extra` into the staging buffer (every item signals)
+            mbar_wait(&ext_full[warp], ext_phase);
+            ext_phase ^= 1;
+        }
         if (active) {
             if (scale_needed && !scale_later) {
 #pragma unroll
@@ -507,7 +530,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 const uint32_t o0 = ring_elem(r0w), o1 = ring_elem(r0w + 1);
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
-                    const double2 e = with_extra ? ex[FUSED ? mt : 0] : make_double2(0.0, 0.0);
+                    double2 e = make_double2(0.0, 0.0);
+                    if (with_extra) e = XT ? *reinterpret_cast<const double2*>(sq + mt * 32) : ex[(FUSED && !HELP) ? mt : 0];
                     const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
                     const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
                     acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
@@ -622,10 +646,13 @@ static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     if (rc) return rc;
     rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, TI) : (tmap_out = tmap, SBP_OK);
     if (rc) return rc;
+    CUtensorMap tmap_ex = tmap_out;  // fused stage update with an extra operand: its quads travel like the output's
+    if (FUSED && HELP && p.extra && p.cb != 0.0) rc = make_tmap(&tmap_ex, p.extra, p.N, p.B, 4, TI);
+    if (rc) return rc;
     SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (p.B + TI - 1) / TI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count));
-    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out);
+    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out, tmap_ex);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
@@ -681,10 +708,11 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     }
     // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
     const int cw = (forced_cw == 12 && out != 0 && !p.fused) ? 12 : (help && out == 2) ? 9 : 8;
-    // fused stage updates: helper variant of an RHS launch, and only without the extra operand (measured, N = 1296: stage
-    // 0.287 vs 0.303 ms on k_bsr without it, but 0.527 vs 0.414 ms with it: 128 registers per thread are too few for the
-    // prefetched operand)
-    if (p.fused && (cw != 9 || satmode == 0 || p.cb != 0.0)) return false;
+    // fused stage updates: helper variant of an RHS launch (the extra operand travels through the staging buffers: the
+    // helpers fetch its quads by TMA as soon as the previous block's results have been read out)
+    // (measured: 2D RHS N = 1296 0.362 ms per stage with the extra operand against 0.414 on k_bsr; 1D RHS N = 101 0.279 against
+    // 0.240 -> those stay on k_bsr)
+    if (p.fused && (cw != 9 || satmode == 0 || (satmode == 2 && p.cb != 0.0))) return false;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;
