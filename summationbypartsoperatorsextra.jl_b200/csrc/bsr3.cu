@@ -696,16 +696,11 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const int enabled = ev ? atoi(ev) : -1;
     if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
     if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N))) return false;
-    static int forced_cw = -1;
-    if (forced_cw < 0) {
-        const char* e = getenv("SBP_BSR_CW");
-        forced_cw = e ? atoi(e) : 8;
-    }
-    static int help = -1;
-    if (help < 0) {
-        const char* e = getenv("SBP_BSR_HELP");
-        help = e ? atoi(e) : 1;
-    }
+    // (read at every launch: the tests switch them)
+    const char* ecw = getenv("SBP_BSR_CW");
+    const int forced_cw = ecw ? atoi(ecw) : 8;
+    const char* eh = getenv("SBP_BSR_HELP");
+    const int help = eh ? atoi(eh) : 1;
     // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
     const int cw = (forced_cw == 12 && out != 0 && !p.fused) ? 12 : (help && out == 2) ? 9 : 8;
     // fused stage updates: helper variant of an RHS launch (the extra operand travels through the staging buffers: the

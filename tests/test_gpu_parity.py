@@ -224,10 +224,14 @@ def sparse_kernel(request, monkeypatch):
     return {"bsr3": "bsr_dmma", "bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
 
 
-@pytest.fixture(params=[2, 0])
+@pytest.fixture(params=["helpers", "plain", "cw12", "k_bsr"])
 def bsr_generation(request, monkeypatch):
-    """block-sparse kernel generation: 2 = bsr3.cu forced, 0 = bsr.cu"""
-    monkeypatch.setenv("SBP_BSR_V3", str(request.param))
+    """block-sparse kernel generation / warp organisation: bsr3.cu forced with store-helper warps (the default for RHS
+    launches), without them, with 12 consumer warps, and bsr.cu"""
+    env = {"helpers": {"SBP_BSR_V3": "2"}, "plain": {"SBP_BSR_V3": "2", "SBP_BSR_HELP": "0"},
+           "cw12": {"SBP_BSR_V3": "2", "SBP_BSR_HELP": "0", "SBP_BSR_CW": "12"}, "k_bsr": {"SBP_BSR_V3": "0"}}[request.param]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     return request.param
 
 
