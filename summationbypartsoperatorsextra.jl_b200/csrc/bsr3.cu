@@ -39,6 +39,9 @@
 #ifndef SBP_B3_PING
 #define SBP_B3_PING 0  // 1: the two consumer warps of a scheduler take turns on the tensor pipe (token through named barriers)
 #endif
+#ifndef SBP_B3_HELPER_FENCE
+#define SBP_B3_HELPER_FENCE 0  // 1: the proxy fence before a TMA store is executed by the helper thread that issues the store
+#endif
 #ifndef SBP_B3_DEFER
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
                     for (int k = 0; k < 2; k++) {
                         const int w = h + 4 * k;
-                        mbar_wait(&out_full[w], ph);
+                        mbar_wait(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
+                        if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
                         const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
                         if (rowA[k] < N) {
                             tma_store_2d(&tmap_out, rowA[k], b0, so);
@@ -558,9 +562,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             if (active) {
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
-                fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
+                if (!SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
             }
-            __syncwarp();
+            __syncwarp();  // orders the lanes' stores before lane 0's arrive (release)
             if (lane == 0) mbar_arrive(&out_full[warp]);
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
