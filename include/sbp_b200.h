@@ -54,12 +54,16 @@ typedef struct sbp_op sbp_op;   /* immutable device-resident operator           
 /* flags for sbp_op_dense_create */
 #define SBP_DENSE_AUTO 0        /* pick kernel from N (smem-resident DMMA tiles or tiled DGEMM)  */
 #define SBP_DENSE_FORCE_GEMM 1  /* always use the tiled DGEMM path                                */
-#define SBP_DENSE_NO_SYMMETRY 2 /* do not exploit centro-antisymmetry even if D has it exactly     */
-/* By default the even/odd kernel is used only when D[N-1-i][N-1-j] == -D[i][j] holds BITWISE for all i, j
- * (then it is the same operator, only the summation order differs).  With SBP_DENSE_SYMMETRIZE the antisymmetric
- * part (D - J D J)/2 is used when |D + J D J|_max <= 256 eps |D|_max (operators that are centro-antisymmetric up to
- * the rounding of their construction, e.g. a barycentric Legendre matrix); entries change by that amount. */
+#define SBP_DENSE_NO_SYMMETRY 2 /* do not exploit centro-antisymmetry even if D has it                 */
+/* Centro-antisymmetric operators (D[N-1-i][N-1-j] == -D[i][j]: Legendre bases on symmetric nodes, classical FD-SBP)
+ * run on the even/odd kernel (half the FP64 work).  The symmetry is accepted when |D + J D J|_max <= 256 eps |D|_max,
+ * i.e. also for a matrix that has it only up to the rounding of its construction, such as the barycentric matrix
+ * `basis.D` of PolynomialBases.jl that src/polynomialbases_operators.jl:148 multiplies by; the antisymmetric part
+ * (D - J D J)/2 is then used, which changes entries by at most 128 eps |D|_max (results move by ~1e-14 relative at
+ * N = 64, far inside the 1e-12 contract).  SBP_DENSE_SYMMETRIZE (the former opt-in) is accepted and implied;
+ * SBP_DENSE_SYM_BITWISE takes the fast path only when the symmetry holds bitwise (same operator, other summation order). */
 #define SBP_DENSE_SYMMETRIZE 4
+#define SBP_DENSE_SYM_BITWISE 16
 /* Small dense operators whose (4-column x 8-row) fragments are >= 25% structurally zero (banded FSBP / FD-SBP
  * operators stored dense, block-diagonal sub-cell operators) skip those fragments; exact for finite inputs
  * (0*x == 0), differs for Inf/NaN inputs exactly like the sparse path.  This flag multiplies the stored zeros. */
@@ -165,10 +169,11 @@ int32_t sbp_apply_table(sbp_ctx* ctx, const sbp_op* op, double* dU, const double
                         const int32_t* op_index, double alpha, double beta, double* energy,
                         double* energy_sum);
 
-/* out[b] = sum_i w_i * f(U[i,b], V[i,b]) with mode 0: u, 1: u^2 (abs2), 2: u*v ; out_sum (device, may be
- * NULL) receives the sum over the batch.  Replaces integrate(func, u, D)
- * (src/polynomialbases_operators.jl:66-68, src/subcell_operators.jl:92-94) and the P-weighted sums of
- * analyze_quantities.  V may be NULL for modes 0/1. */
+/* out[b] = sum_i w_i * f(U[i,b], V[i,b]) with mode 0: u, 1: u^2 (abs2), 2: u*v, 3: |u| (abs), 16 + k: u^k for an
+ * integer 0 <= k < 64 (x -> x^k, evaluated by binary powering like Julia's power_by_squaring); out_sum (device, may be
+ * NULL) receives the sum over the batch.  Replaces integrate(func, u, D) (src/polynomialbases_operators.jl:66-68,
+ * src/subcell_operators.jl:92-94; the reference accepts any `func`, the device these) and the P-weighted sums of
+ * analyze_quantities.  V may be NULL except for mode 2. */
 int32_t sbp_integrate(sbp_ctx* ctx, const sbp_op* op, const double* U, const double* V, int64_t B,
                       int32_t mode, double* out, double* out_sum);
 
@@ -225,12 +230,35 @@ int32_t sbp_comm_init(sbp_ctx* ctx, int32_t nranks, int32_t rank, const char id[
 int32_t sbp_allreduce_sum(sbp_ctx* ctx, double* dptr, int32_t count); /* ncclAllReduce(double, sum), in place */
 int32_t sbp_comm_destroy(sbp_ctx* ctx);
 
-/* ---- host-buffer convenience (end-to-end path: pinned staging + chunked H2D/compute/D2H overlap) */
+/* ---- device-resident time stepping ------------------------------------------------------------------- */
+/* Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive = false)`, examples/RBF_FSBP_advection.jl:45-51) on a batch that
+ * never leaves the device: nsteps steps of sizes h_steps[s] (HOST array), five sbp_rhs_advection{2d,1d}_stage launches per
+ * step.  `op` is a 2D or 1D advection bundle; U (device, B*N) holds u(t0) on entry and u(t_end) on return.  bc_table
+ * (device): boundary data of every stage, row 5*s + k = data of stage k of step s at time t_s + c_k h_s
+ * (c = 0, 0.377268915331368, 0.754537830662736, 0.728985661612188, 0.699226135931670), rows bc_row_stride doubles apart,
+ * each holding what sbp_rhs_advection2d takes as `g` (N doubles, shared by the batch) resp. sbp_rhs_advection1d as `bc`
+ * (2 doubles).  work: 3*B*N doubles of device scratch, or NULL (library-owned, grown on demand). */
+int32_t sbp_solve_ssprk53(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const double* bc_table,
+                          int64_t bc_row_stride, int64_t nsteps, const double* h_steps, double* work);
+
+/* ---- host-buffer entry points (end-to-end path: pinned staging + chunked H2D/compute/D2H overlap) ------- */
 /* h_dU = alpha*scale*D*h_U + beta*h_dU for host arrays; copies are pipelined in chunks of
  * `chunk_instances` (0 = auto) over three streams.  This is what `mul!(dU::Matrix, D, U::Matrix)` on
  * host arrays maps to. */
 int32_t sbp_apply_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B,
                        double alpha, double beta, int64_t chunk_instances);
+/* The 2D advection RHS `semi(du, u, p, t)` (src/conservation_laws/multidimensional_linear_advection.jl:73-81) for HOST
+ * matrices: h_g holds the boundary data as for sbp_rhs_advection2d but in host memory (N doubles when g_stride == 0, else
+ * row b at h_g + b*g_stride); same chunked pipeline as sbp_apply_host. */
+int32_t sbp_rhs_advection2d_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B,
+                                 const double* h_g, int64_t g_stride, int64_t chunk_instances);
+/* sbp_solve_ssprk53 for a HOST state and HOST boundary table: one upload of u(t0) and the table, nsteps steps on the device,
+ * one download of u(t_end) -- the end-to-end form of a whole solve. */
+int32_t sbp_solve_ssprk53_host(sbp_ctx* ctx, const sbp_op* op, double* h_U, int64_t B, const double* h_bc_table,
+                               int64_t bc_row_stride, int64_t nsteps, const double* h_steps);
+/* Pinned-memory cudaMemcpyAsync rates of this box (GB/s): H2D alone, D2H alone, both directions at once (sum) -- the
+ * ceiling of the *_host entry points (they move 8 B/DOF each way). */
+int32_t sbp_pcie_probe(sbp_ctx* ctx, size_t bytes, double* h2d_gbs, double* d2h_gbs, double* bidir_gbs);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ from .operators import (DerivativeOperator, GaussLegendre, GaussRadauLeft, Gauss
                         OperatorTable, PolynomialBasesDerivativeOperator, SubcellOperator, abs2, couple_subcell,
                         find_corners, grid, identity, integrate, interpolation_matrix, legendre_derivative_operator,
                         mass_matrix, mass_matrix_boundary, mattsson_nordstrom_2004, mul_,
-                        neighborhood_sparsity_pattern, polynomialbases_derivative_operator,
+                        neighborhood_sparsity_pattern, polynomialbases_derivative_operator, power,
                         scale_by_inverse_mass_matrix_, scale_by_mass_matrix_, tensor_product_operator_2D,
                         upload_csr, upload_dense, upload_sparse, upload_table)
 from .conservation_laws import (AnalysisCallback, MultidimensionalLinearAdvectionNonperiodicSemidiscretization,

@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 SBP_OK, SBP_EINVAL, SBP_EDIM, SBP_ECUDA, SBP_ENOMEM, SBP_ENCCL, SBP_EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 OP_DENSE, OP_SPARSE, OP_TABLE, OP_ADVECTION2D, OP_ADVECTION1D = 1, 2, 3, 4, 5
-DENSE_AUTO, DENSE_FORCE_GEMM, DENSE_NO_SYMMETRY, DENSE_SYMMETRIZE, DENSE_NO_SKIP = 0, 1, 2, 4, 8
+DENSE_AUTO, DENSE_FORCE_GEMM, DENSE_NO_SYMMETRY, DENSE_SYMMETRIZE, DENSE_NO_SKIP, DENSE_SYM_BITWISE = 0, 1, 2, 4, 8, 16
 KERNEL_NAMES = {1: "dmma_smem", 2: "dmma_smem_sym", 3: "dgemm_tiled", 4: "csr_smem", 5: "table_generic", 6: "bsr_dmma"}
 NCCL_ID_BYTES = 128
 
@@ -101,6 +101,10 @@ SIGNATURES = {
     "sbp_allreduce_sum": (c_i32, [c_void_p, c_void_p, c_i32]),
     "sbp_comm_destroy": (c_i32, [c_void_p]),
     "sbp_apply_host": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, c_i64]),
+    "sbp_rhs_advection2d_host": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64]),
+    "sbp_solve_ssprk53": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
+    "sbp_solve_ssprk53_host": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p]),
+    "sbp_pcie_probe": (c_i32, [c_void_p, c_size_t, P(c_dbl), P(c_dbl), P(c_dbl)]),
 }
 
 

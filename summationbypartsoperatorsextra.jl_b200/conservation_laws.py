@@ -33,7 +33,11 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
     """u_t + a . grad u = 0 with boundary data bc(x, t)
     (src/conservation_laws/multidimensional_linear_advection.jl:10-42)."""
 
-    def __init__(self, derivative: MultidimensionalMatrixDerivativeOperator, a, bc, storage: str | None = None):
+    def __init__(self, derivative: MultidimensionalMatrixDerivativeOperator, a, bc, storage: str | None = None,
+                 bc_vectorized: bool = False):
+        """`bc_vectorized=True` declares that `bc(x, t)` accepts coordinate ARRAYS (x = (xs, ys), one entry per inflow
+        node) and returns the array of boundary values; the first evaluation is checked against the node-by-node call at
+        every inflow node.  By default `bc` is called node by node, as the reference's `set_bc!` does (:65-66)."""
         if len(a) != 2 or len(derivative.Ds) != 2:
             raise ArgumentError("Only 2D is supported")  # "Only support 2D for now" (:30)
         D = derivative
@@ -54,6 +58,7 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
         self.bnd_tau = D.weights_boundary * an  # tau_i of analyze_quantities (:101-103)
         self._dev: dict[int, tuple] = {}
         self._g_cache: dict[int, tuple] = {}
+        self._bc_vectorized, self._bc_checked = bool(bc_vectorized), False
 
     # -- device bundle ----------------------------------------------------------------------------------
     def _want_sparse(self, A):
@@ -83,25 +88,24 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
         return ent[0]
 
     def boundary_values(self, t: float) -> np.ndarray:
-        """g_j = bc(x_j, t) at inflow nodes (0 elsewhere) -- the data `set_bc!` writes into tmp1 (:65-66).  A boundary
-        function that accepts coordinate arrays (x = (xs, ys)) is evaluated once for all inflow nodes, any other one
-        node by node."""
+        """g_j = bc(x_j, t) at inflow nodes (0 elsewhere) -- the data `set_bc!` writes into tmp1 (:65-66).  `bc` is called
+        node by node unless the semidiscretization was built with `bc_vectorized=True` (one call with coordinate arrays,
+        validated against the scalar calls at every inflow node the first time; a mismatch raises)."""
         g = np.zeros(self.derivative.N)
         nodes = self.derivative.grid
         idx = np.asarray(self.inflow_nodes, dtype=np.int64)
         if idx.size == 0:
             return g
-        vals = None
-        if getattr(self, "_bc_vectorised", True):
-            try:
-                v = np.asarray(self.bc(nodes[idx].T, t), dtype=np.float64)
-                j0 = int(idx[0])
-                if v.shape == (idx.size,) and v[0] == float(self.bc(nodes[j0], t)):
-                    vals = v
-            except Exception:
-                pass
-            self._bc_vectorised = vals is not None
-        if vals is None:
+        if self._bc_vectorized:
+            vals = np.asarray(self.bc(nodes[idx].T, t), dtype=np.float64)
+            if vals.shape != (idx.size,):
+                raise ArgumentError(f"bc_vectorized: bc returned shape {vals.shape}, expected ({idx.size},)")
+            if not self._bc_checked:
+                ref = np.array([float(self.bc(nodes[j], t)) for j in idx])
+                if not np.allclose(vals, ref, rtol=1e-13, atol=1e-300):
+                    raise ArgumentError("bc_vectorized: the array call of bc disagrees with its node-by-node evaluation")
+                self._bc_checked = True
+        else:
             vals = [self.bc(nodes[j], t) for j in idx]
         g[idx] = vals
         return g
@@ -137,6 +141,20 @@ class MultidimensionalLinearAdvectionNonperiodicSemidiscretization(AbstractSemid
             gptr, gstride = g.ptr, N
         check(ctx._lib.sbp_rhs_advection2d(ctx.handle, op.handle, _ptr(du.ptr), _ptr(u.ptr), u.B, _ptr(gptr),
                                            gstride, _ptr(quantities.ptr) if quantities is not None else None))
+        return None
+
+    def rhs_host(self, ctx: Context, hdu: np.ndarray, hu: np.ndarray, t: float = 0.0, chunk_instances: int = 0):
+        """`semi(du, u, p, t)` for HOST matrices (B, N): chunks travel H2D -> fused RHS kernel -> D2H through the library's
+        pinned-staging pipeline (`sbp_rhs_advection2d_host`).  Use `ctx.pinned_empty` arrays for full copy speed."""
+        N = self.derivative.N
+        if hu.ndim != 2 or hu.shape[1] != N or hdu.shape != hu.shape:
+            raise DimensionMismatch("du, u and the operator differ in size")
+        if not (hu.flags.c_contiguous and hdu.flags.c_contiguous and hu.dtype == np.float64 and hdu.dtype == np.float64):
+            raise ArgumentError("host batches must be C-contiguous float64 arrays")
+        g = _as_f64(self.boundary_values(float(t)))
+        check(ctx._lib.sbp_rhs_advection2d_host(ctx.handle, self.device_op(ctx).handle, hdu.ctypes.data_as(C.c_void_p),
+                                                hu.ctypes.data_as(C.c_void_p), hu.shape[0], g.ctypes.data_as(C.c_void_p),
+                                                0, int(chunk_instances)))
         return None
 
     def stage(self, unext: DeviceBatch, u: DeviceBatch, t: float, ca: float, ch: float, cb: float = 0.0,
@@ -289,22 +307,37 @@ class AnalysisCallback:
         self.semi, self.interval, self.dt = semi, int(interval), dt
         self._tstops: list[float] = []
         self._quantities: list[np.ndarray] = []
-        self._next_t = None
+        self._t0, self._k = None, 0
 
     def __call__(self, du, u, p, t):
         self._tstops.append(float(t))
         self._quantities.append(analyze_quantities(self.semi, du, u, p, t))
 
     def should_fire(self, step: int, t: float, final: bool) -> bool:
+        """interval mode: a DiscreteCallback without `initialize` -- checked after every accepted step, so the first record
+        comes after `interval` steps, not at step 0 (analysis_callback.jl:85-105).  dt mode: a PeriodicCallback with
+        initial_affect and final_affect: records at t0, at every t0 + k dt (the driver clips its steps to land on them,
+        `stop_times`) and at the final time."""
         if self.dt is not None:
-            if self._next_t is None:
-                self._next_t = t  # initial_affect = true
-            if t >= self._next_t - 1e-12 or final:
-                while self._next_t <= t + 1e-12:
-                    self._next_t += self.dt
+            if self._t0 is None:
+                self._t0, self._k = t, 0  # initial_affect = true
                 return True
-            return False
-        return self.interval > 0 and (step % self.interval == 0 or final)
+            hit = False
+            while self._t0 + (self._k + 1) * self.dt <= t + 1e-12 * max(1.0, abs(t)):
+                self._k += 1
+                hit = True
+            return hit or final
+        return self.interval > 0 and step > 0 and (step % self.interval == 0 or final)
+
+    def stop_times(self, t0: float, tend: float) -> list[float]:
+        """The tstops a PeriodicCallback adds (multiples of dt after t0, inside the time span); empty in interval mode."""
+        if self.dt is None:
+            return []
+        out, k = [], 1
+        while t0 + k * self.dt < tend - 1e-12 * max(1.0, abs(tend)):
+            out.append(t0 + k * self.dt)
+            k += 1
+        return out
 
     def __repr__(self):
         return f"AnalysisCallback(interval={self.interval}, dt={self.dt})"
@@ -325,62 +358,84 @@ _SSPRK53 = dict(
     c1=0.377268915331368, c2=0.754537830662736, c3=0.728985661612188, c4=0.699226135931670)
 
 
+def step_schedule(t0: float, tend: float, dt: float, stops=()) -> list[tuple[float, float]]:
+    """(t, h) of every step of a fixed-step integration from t0 to tend: steps of size dt, clipped so that the integrator
+    lands exactly on each stop time (the tstops a PeriodicCallback adds) and on tend, as OrdinaryDiffEq does."""
+    marks = sorted(float(x) for x in stops if t0 < x < tend) + [float(tend)]
+    out, t, mi = [], float(t0), 0
+    while mi < len(marks):
+        nxt = marks[mi]
+        if nxt - t <= 1e-14 * max(1.0, abs(nxt)):
+            mi += 1
+            continue
+        h = dt
+        if t + h >= nxt - 1e-12 * max(1.0, abs(nxt)):  # the step would reach or pass the mark: land on it exactly
+            out.append((t, nxt - t))
+            t = nxt
+            mi += 1
+        else:
+            out.append((t, h))
+            t += h
+    return out
+
+
 def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None = None) -> DeviceBatch:
     """Fixed-step SSPRK53 (`solve(ode, SSPRK53(); dt, adaptive=false)`, examples/RBF_FSBP_advection.jl:45-51), device
-    resident: every stage is ONE call -- the stage update rides on the RHS pass (`semi.stage`, sbp_rhs_advection*_stage:
-    104 B/DOF per step on the block-sparse kernel instead of 80 + 144 with separate RHS and update passes).  Semi-
-    discretizations without a `stage` method take the RHS + `lincomb_` route.  Returns the final state."""
+    resident: the time loop runs inside the library (`sbp_solve_ssprk53`), every stage is ONE launch -- the stage update
+    rides on the RHS pass (sbp_rhs_advection*_stage: 104 B/DOF per step on the block-sparse kernel instead of 80 + 144 with
+    separate RHS and update passes).  Semidiscretizations without device boundary tables take the RHS + `lincomb_` route.
+    Returns the final state."""
     k = _SSPRK53
     u: DeviceBatch = prob.u0
     semi, p = prob.f, prob.p
-    t, tend = float(prob.tspan[0]), float(prob.tspan[1])
-    u1, u2, u3 = u.similar(), u.similar(), u.similar()
+    t0, tend = float(prob.tspan[0]), float(prob.tspan[1])
     u = u.copy()
-    fused = hasattr(semi, "stage")
-    du = u.similar() if (callback is not None or not fused) else None
-    step = 0
-    if callback is not None and callback.should_fire(step, t, False):
-        callback(du, u, p, t)
-    table, trow, tstride = None, 0, 0  # boundary data of the next steps' stage times, uploaded 64 steps at a time
+    steps = step_schedule(t0, tend, dt, callback.stop_times(t0, tend) if callback is not None else ())
     cs = (0.0, k["c1"], k["c2"], k["c3"], k["c4"])
-    while t < tend - 1e-14:
-        h = min(dt, tend - t)
-        if fused:
-            gp = [None] * 5
-            if hasattr(semi, "boundary_table"):
-                if table is None or trow + 5 > tstride:
-                    if table is not None:
-                        table[0].free()
-                    times, tt = [], t
-                    while tt < tend - 1e-14 and len(times) < 5 * 64:
-                        hh = min(dt, tend - tt)
-                        times += [tt + c * hh for c in cs]
-                        tt += hh
-                    buf = semi.boundary_table(u.ctx, times)
-                    table, trow, tstride = (buf, buf.nbytes // max(len(times), 1)), 0, len(times)
-                gp = [table[0].ptr + (trow + i) * table[1] for i in range(5)]
-                trow += 5
-            semi.stage(u1, u, t, 1.0, k["b10"] * h, gptr=gp[0])                                   # u1 = u + b10 h f(u)
-            semi.stage(u2, u1, t + k["c1"] * h, 1.0, k["b21"] * h, gptr=gp[1])                    # u2 = u1 + b21 h f(u1)
-            semi.stage(u3, u2, t + k["c2"] * h, k["a32"], k["b32"] * h, k["a30"], u, gptr=gp[2])  # u3 = a30 u + a32 u2 + b32 h f(u2)
-            semi.stage(u1, u3, t + k["c3"] * h, k["a43"], k["b43"] * h, k["a40"], u, gptr=gp[3])  # u4 (in u1)
-            semi.stage(u, u1, t + k["c4"] * h, k["a54"], k["b54"] * h, k["a52"], u2, gptr=gp[4])  # u5 = a52 u2 + a54 u4 + b54 h f(u4)
-        else:
-            semi(du, u, p, t)
-            u1.lincomb_(1.0, u, k["b10"] * h, du)
-            semi(du, u1, p, t + k["c1"] * h)
-            u2.lincomb_(1.0, u1, k["b21"] * h, du)
-            semi(du, u2, p, t + k["c2"] * h)
-            u3.lincomb_(k["a30"], u, k["a32"], u2, k["b32"] * h, du)
-            semi(du, u3, p, t + k["c3"] * h)
-            u1.lincomb_(k["a40"], u, k["a43"], u3, k["b43"] * h, du)
-            semi(du, u1, p, t + k["c4"] * h)
-            u.lincomb_(k["a52"], u2, k["a54"], u1, k["b54"] * h, du)
-        t += h
-        step += 1
-        if callback is not None and callback.should_fire(step, t, t >= tend - 1e-14):
-            callback(du, u, p, t)
-    if table is not None:
-        u.ctx.synchronize()
-        table[0].free()
+    if hasattr(semi, "boundary_table"):
+        # device-resident: the library runs whole runs of steps (sbp_solve_ssprk53); the host only evaluates the boundary
+        # functions (64 steps per upload) and comes back where the analysis callback fires
+        ctx = u.ctx
+        op = semi.device_op(ctx)
+        du = u.similar() if callback is not None else None
+        if callback is not None and callback.should_fire(0, t0, False):
+            callback(du, u, p, t0)
+        fires = [callback is not None and callback.should_fire(si + 1, steps[si + 1][0] if si + 1 < len(steps) else tend,
+                                                               si + 1 == len(steps)) for si in range(len(steps))]
+        si = 0
+        while si < len(steps):
+            sj = si
+            while sj < len(steps) and sj - si < 64:
+                sj += 1
+                if fires[sj - 1]:
+                    break
+            seg = steps[si:sj]
+            table = semi.boundary_table(ctx, [tt + c * hh for (tt, hh) in seg for c in cs])
+            row = table.nbytes // (5 * len(seg)) // 8
+            hs = np.ascontiguousarray([hh for (_, hh) in seg], dtype=np.float64)
+            check(ctx._lib.sbp_solve_ssprk53(ctx.handle, op.handle, _ptr(u.ptr), u.B, _ptr(table.ptr), row, len(seg),
+                                             hs.ctypes.data_as(C.c_void_p), None))
+            ctx.synchronize()
+            table.free()
+            if fires[sj - 1]:
+                callback(du, u, p, steps[sj][0] if sj < len(steps) else tend)
+            si = sj
+        return u
+    u1, u2, u3, du = u.similar(), u.similar(), u.similar(), u.similar()
+    if callback is not None and callback.should_fire(0, t0, False):
+        callback(du, u, p, t0)
+    for si, (t, h) in enumerate(steps):
+        semi(du, u, p, t)
+        u1.lincomb_(1.0, u, k["b10"] * h, du)
+        semi(du, u1, p, t + k["c1"] * h)
+        u2.lincomb_(1.0, u1, k["b21"] * h, du)
+        semi(du, u2, p, t + k["c2"] * h)
+        u3.lincomb_(k["a30"], u, k["a32"], u2, k["b32"] * h, du)
+        semi(du, u3, p, t + k["c3"] * h)
+        u1.lincomb_(k["a40"], u, k["a43"], u3, k["b43"] * h, du)
+        semi(du, u1, p, t + k["c4"] * h)
+        u.lincomb_(k["a52"], u2, k["a54"], u1, k["b54"] * h, du)
+        tn = steps[si + 1][0] if si + 1 < len(steps) else tend
+        if callback is not None and callback.should_fire(si + 1, tn, si + 1 == len(steps)):
+            callback(du, u, p, tn)
     return u

@@ -170,8 +170,11 @@ static int32_t build_dense(sbp_op* op, int N, int G, const double* h_D, int ldd,
                         dev = std::max(dev, std::fabs(at(i, k) + at(N - 1 - i, N - 1 - k)));
                         amax = std::max(amax, std::fabs(at(i, k)));
                     }
+                // centro-antisymmetric up to the rounding of its construction (a barycentric Legendre matrix as
+                // PolynomialBases.jl builds it: deviation ~1e-16 |D|max): the antisymmetric part (D - J D J)/2 is used.
+                // SBP_DENSE_SYM_BITWISE restricts the fast path to matrices that have the symmetry bitwise.
                 const bool exact = dev == 0.0;
-                const bool approx = (flags & SBP_DENSE_SYMMETRIZE) && dev <= 256.0 * 2.220446049250313e-16 * amax;
+                const bool approx = !(flags & SBP_DENSE_SYM_BITWISE) && dev <= 256.0 * 2.220446049250313e-16 * amax;
                 // the even/odd split halves the work; skipping zero fragments wins when more than half are zero
                 const bool prefer_skip = op->band > 0 && (2.0 * op->band + 1.0) / NT < 0.5;
                 if ((exact || approx) && !prefer_skip) {
@@ -591,6 +594,82 @@ static int32_t load_nccl() {
     return SBP_OK;
 }
 
+// ---- host-buffer pipeline -----------------------------------------------------------------------------
+// Chunks of instances travel H2D -> kernel -> D2H over three streams with two staging slots.  `run` launches the hot-path
+// call for nb instances starting at instance `done` on device buffers (dIn -> dOut) on the ctx stream.
+template <typename Run>
+static int32_t host_pipeline(sbp_ctx* ctx, int N, int G, double* h_out, const double* h_in, int64_t B, bool read_out,
+                             int64_t chunk_instances, Run run) {
+    if (chunk_instances <= 0) chunk_instances = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)N * 8));
+    // keep chunks a multiple of 128*G so that table periodicity and kernel tiling are preserved
+    const int64_t q = 128 * (int64_t)G;
+    chunk_instances = std::max<int64_t>(q, (chunk_instances / q) * q);
+    chunk_instances = std::min<int64_t>(chunk_instances, ((B + q - 1) / q) * q);
+    const size_t cbytes = (size_t)chunk_instances * N * sizeof(double);
+    if (ctx->pipe_bytes < cbytes) {
+        SBP_CUDA(cudaDeviceSynchronize());
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 2; k++) {
+                if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
+                ctx->pipe_dev[s][k] = nullptr;
+            }
+        ctx->pipe_bytes = 0;
+        for (int s = 0; s < 2; s++)
+            for (int k = 0; k < 2; k++) SBP_CUDA(cudaMalloc(&ctx->pipe_dev[s][k], cbytes));
+        ctx->pipe_bytes = cbytes;
+    }
+    cudaStream_t compute = ctx->stream;
+    // the pipeline must start after work already queued on the compute stream
+    SBP_CUDA(cudaEventRecord(ctx->pipe_ev[0][2], compute));
+    SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[0][2], 0));
+    SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[0][2], 0));
+    int64_t done = 0;
+    int c = 0;
+    enum { EV_IN = 0, EV_COMP = 1, EV_OUT = 2 };
+    bool used[2] = {false, false};
+    while (done < B) {
+        const int s = c & 1;
+        const int64_t nb = std::min<int64_t>(chunk_instances, B - done);
+        const size_t bytes = (size_t)nb * N * sizeof(double);
+        double* dIn = static_cast<double*>(ctx->pipe_dev[s][0]);
+        double* dOut = static_cast<double*>(ctx->pipe_dev[s][1]);
+        if (used[s]) {
+            SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_COMP], 0));  // dIn[s] consumed
+            if (read_out) SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_OUT], 0));
+        }
+        SBP_CUDA(cudaMemcpyAsync(dIn, h_in + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        if (read_out) SBP_CUDA(cudaMemcpyAsync(dOut, h_out + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_IN], ctx->s_in));
+        SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_IN], 0));
+        if (used[s]) SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_OUT], 0));  // dOut[s] drained
+        int32_t rc = run(dOut, dIn, nb, done);
+        if (rc) return rc;
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_COMP], compute));
+        SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[s][EV_COMP], 0));
+        SBP_CUDA(cudaMemcpyAsync(h_out + done * N, dOut, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
+        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_OUT], ctx->s_out));
+        used[s] = true;
+        done += nb;
+        c++;
+    }
+    SBP_CUDA(cudaStreamSynchronize(ctx->s_out));
+    SBP_CUDA(cudaStreamSynchronize(compute));
+    return SBP_OK;
+}
+
+// grow-only device buffer owned by the ctx (boundary data / work vectors of the *_host and solve entry points)
+static int32_t ensure_aux(sbp_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (ctx->aux_bytes[slot] < bytes) {
+        SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->aux[slot]) cudaFree(ctx->aux[slot]);
+        ctx->aux[slot] = nullptr, ctx->aux_bytes[slot] = 0;
+        SBP_CUDA(cudaMalloc(&ctx->aux[slot], bytes));
+        ctx->aux_bytes[slot] = bytes;
+    }
+    *out = ctx->aux[slot];
+    return SBP_OK;
+}
+
 }  // namespace sbp
 
 using namespace sbp;
@@ -668,6 +747,8 @@ int32_t sbp_ctx_destroy(sbp_ctx* ctx) {
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage_buf) cudaFree(ctx->stage_buf);
+    for (void* a : ctx->aux)
+        if (a) cudaFree(a);
     for (int s = 0; s < 2; s++) {
         for (int k = 0; k < 2; k++)
             if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
@@ -1262,7 +1343,7 @@ int32_t sbp_comm_destroy(sbp_ctx* ctx) {
     return SBP_OK;
 }
 
-// ---- host-buffer pipeline -----------------------------------------------------------------------------
+// ---- host-buffer entry points ---------------------------------------------------------------------------
 int32_t sbp_apply_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B, double alpha,
                        double beta, int64_t chunk_instances) {
     SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
@@ -1270,63 +1351,150 @@ int32_t sbp_apply_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const doubl
     if (B == 0) return SBP_OK;
     SBP_REQUIRE(h_dU && h_U, SBP_EINVAL, "null host buffer");
     SBP_CUDA(cudaSetDevice(ctx->device));
+    return host_pipeline(ctx, op->N, op->G, h_dU, h_U, B, beta != 0.0, chunk_instances,
+                         [&](double* dOut, const double* dIn, int64_t nb, int64_t) {
+                             return sbp_apply(ctx, op, dOut, dIn, nb, alpha, beta);
+                         });
+}
+
+int32_t sbp_rhs_advection2d_host(sbp_ctx* ctx, const sbp_op* op, double* h_dU, const double* h_U, int64_t B,
+                                 const double* h_g, int64_t g_stride, int64_t chunk_instances) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION2D, SBP_EINVAL, "not a 2D advection bundle");
+    SBP_REQUIRE(B >= 0, SBP_EDIM, "negative batch size");
+    if (B == 0) return SBP_OK;
+    SBP_REQUIRE(h_dU && h_U && h_g, SBP_EINVAL, "null host buffer");
+    SBP_REQUIRE(g_stride == 0 || g_stride >= op->N, SBP_EDIM, "g_stride must be 0 or >= N");
+    SBP_CUDA(cudaSetDevice(ctx->device));
     const int N = op->N;
-    const int G = op->G;
-    if (chunk_instances <= 0) chunk_instances = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)N * 8));
-    // keep chunks a multiple of 128*G so that table periodicity and kernel tiling are preserved
-    const int64_t q = 128 * (int64_t)G;
-    chunk_instances = std::max<int64_t>(q, (chunk_instances / q) * q);
-    chunk_instances = std::min<int64_t>(chunk_instances, ((B + q - 1) / q) * q);
-    const size_t cbytes = (size_t)chunk_instances * N * sizeof(double);
-    if (ctx->pipe_bytes < cbytes) {
-        SBP_CUDA(cudaDeviceSynchronize());
-        for (int s = 0; s < 2; s++)
-            for (int k = 0; k < 2; k++) {
-                if (ctx->pipe_dev[s][k]) cudaFree(ctx->pipe_dev[s][k]);
-                ctx->pipe_dev[s][k] = nullptr;
-            }
-        ctx->pipe_bytes = 0;
-        for (int s = 0; s < 2; s++)
-            for (int k = 0; k < 2; k++) SBP_CUDA(cudaMalloc(&ctx->pipe_dev[s][k], cbytes));
-        ctx->pipe_bytes = cbytes;
-    }
-    cudaStream_t compute = ctx->stream;
-    // the pipeline must start after work already queued on the compute stream
-    SBP_CUDA(cudaEventRecord(ctx->pipe_ev[0][2], compute));
-    SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[0][2], 0));
-    SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[0][2], 0));
-    int64_t done = 0;
-    int c = 0;
-    enum { EV_IN = 0, EV_COMP = 1, EV_OUT = 2 };
-    bool used[2] = {false, false};
-    while (done < B) {
-        const int s = c & 1;
-        const int64_t nb = std::min<int64_t>(chunk_instances, B - done);
-        const size_t bytes = (size_t)nb * N * sizeof(double);
-        double* dIn = static_cast<double*>(ctx->pipe_dev[s][0]);
-        double* dOut = static_cast<double*>(ctx->pipe_dev[s][1]);
-        if (used[s]) {
-            SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_COMP], 0));  // dIn[s] consumed
-            if (beta != 0.0) SBP_CUDA(cudaStreamWaitEvent(ctx->s_in, ctx->pipe_ev[s][EV_OUT], 0));
-        }
-        SBP_CUDA(cudaMemcpyAsync(dIn, h_U + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
-        if (beta != 0.0) SBP_CUDA(cudaMemcpyAsync(dOut, h_dU + done * N, bytes, cudaMemcpyHostToDevice, ctx->s_in));
-        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_IN], ctx->s_in));
-        SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_IN], 0));
-        if (used[s]) SBP_CUDA(cudaStreamWaitEvent(compute, ctx->pipe_ev[s][EV_OUT], 0));  // dOut[s] drained
-        int32_t rc = sbp_apply(ctx, op, dOut, dIn, nb, alpha, beta);
+    // boundary data: shared by the batch (N doubles) or per instance (B rows of g_stride doubles), uploaded once up front
+    const size_t gbytes = (g_stride == 0 ? (size_t)N : (size_t)((B - 1) * g_stride + N)) * sizeof(double);
+    void* d_g = nullptr;
+    int32_t rc = ensure_aux(ctx, 0, gbytes, &d_g);
+    if (rc) return rc;
+    SBP_CUDA(cudaMemcpyAsync(d_g, h_g, gbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return host_pipeline(ctx, N, 1, h_dU, h_U, B, false, chunk_instances,
+                         [&](double* dOut, const double* dIn, int64_t nb, int64_t done) {
+                             return sbp_rhs_advection2d(ctx, op, dOut, dIn, nb,
+                                                        static_cast<const double*>(d_g) + done * g_stride, g_stride, nullptr);
+                         });
+}
+
+// ---- device-resident fixed-step SSPRK53 ---------------------------------------------------------------
+// Shu-Osher form of OrdinaryDiffEq's SSPRK53 (Ruuth 2006), the integrator of examples/RBF_FSBP_advection.jl:45-51
+static const double kSsp[] = {/*a30*/ 0.355909775063327, /*a32*/ 0.644090224936674, /*a40*/ 0.367933791638137,
+                              /*a43*/ 0.632066208361863, /*a52*/ 0.237593836598569, /*a54*/ 0.762406163401431,
+                              /*b10*/ 0.377268915331368, /*b21*/ 0.377268915331368, /*b32*/ 0.242995220537396,
+                              /*b43*/ 0.238458932846290, /*b54*/ 0.287632146308408};
+
+int32_t sbp_solve_ssprk53(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const double* bc_table,
+                          int64_t bc_row_stride, int64_t nsteps, const double* h_steps, double* work) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(op->kind == SBP_OP_ADVECTION2D || op->kind == SBP_OP_ADVECTION1D, SBP_EINVAL,
+                "sbp_solve_ssprk53 needs an advection bundle");
+    SBP_REQUIRE(B >= 0 && nsteps >= 0, SBP_EDIM, "negative batch size / step count");
+    if (B == 0 || nsteps == 0) return SBP_OK;
+    SBP_REQUIRE(U && bc_table && h_steps, SBP_EINVAL, "null argument");
+    const bool two_d = op->kind == SBP_OP_ADVECTION2D;
+    SBP_REQUIRE(bc_row_stride >= (two_d ? op->N : 2), SBP_EDIM, "bc_row_stride too small (%lld)", (long long)bc_row_stride);
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)B * op->N;
+    if (!work) {
+        void* w = nullptr;
+        int32_t rc = ensure_aux(ctx, 1, 3 * n * sizeof(double), &w);
         if (rc) return rc;
-        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_COMP], compute));
-        SBP_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->pipe_ev[s][EV_COMP], 0));
-        SBP_CUDA(cudaMemcpyAsync(h_dU + done * N, dOut, bytes, cudaMemcpyDeviceToHost, ctx->s_out));
-        SBP_CUDA(cudaEventRecord(ctx->pipe_ev[s][EV_OUT], ctx->s_out));
-        used[s] = true;
-        done += nb;
-        c++;
+        work = static_cast<double*>(w);
     }
-    SBP_CUDA(cudaStreamSynchronize(ctx->s_out));
-    SBP_CUDA(cudaStreamSynchronize(compute));
+    double *u = U, *u1 = work, *u2 = work + n, *u3 = work + 2 * n;
+    auto stage = [&](double* unext, const double* uin, const double* bc, double ca, double ch, double cb, const double* extra) {
+        return two_d ? sbp_rhs_advection2d_stage(ctx, op, unext, uin, B, bc, 0, ca, cb, extra, ch)
+                     : sbp_rhs_advection1d_stage(ctx, op, unext, uin, B, bc, 0, ca, cb, extra, ch);
+    };
+    const double* k = kSsp;
+    for (int64_t s = 0; s < nsteps; s++) {
+        const double h = h_steps[s];
+        const double* bc = bc_table + 5 * s * bc_row_stride;
+        int32_t rc = stage(u1, u, bc, 1.0, k[6] * h, 0.0, nullptr);                                   // u1 = u + b10 h f(u)
+        if (!rc) rc = stage(u2, u1, bc + bc_row_stride, 1.0, k[7] * h, 0.0, nullptr);                 // u2 = u1 + b21 h f(u1)
+        if (!rc) rc = stage(u3, u2, bc + 2 * bc_row_stride, k[1], k[8] * h, k[0], u);                 // u3 = a30 u + a32 u2 + b32 h f(u2)
+        if (!rc) rc = stage(u1, u3, bc + 3 * bc_row_stride, k[3], k[9] * h, k[2], u);                 // u4 = a40 u + a43 u3 + b43 h f(u3)
+        if (!rc) rc = stage(u, u1, bc + 4 * bc_row_stride, k[5], k[10] * h, k[4], u2);                // u  = a52 u2 + a54 u4 + b54 h f(u4)
+        if (rc) return rc;
+    }
     return SBP_OK;
+}
+
+int32_t sbp_solve_ssprk53_host(sbp_ctx* ctx, const sbp_op* op, double* h_U, int64_t B, const double* h_bc_table,
+                               int64_t bc_row_stride, int64_t nsteps, const double* h_steps) {
+    SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
+    SBP_REQUIRE(B >= 0 && nsteps >= 0, SBP_EDIM, "negative batch size / step count");
+    if (B == 0) return SBP_OK;
+    SBP_REQUIRE(h_U && (nsteps == 0 || (h_bc_table && h_steps)), SBP_EINVAL, "null argument");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)B * op->N, tbytes = (size_t)(5 * nsteps * bc_row_stride) * sizeof(double);
+    void *d_u = nullptr, *d_t = nullptr;
+    int32_t rc = ensure_aux(ctx, 2, n * sizeof(double), &d_u);
+    if (!rc) rc = ensure_aux(ctx, 0, std::max<size_t>(tbytes, 16), &d_t);
+    if (rc) return rc;
+    SBP_CUDA(cudaMemcpyAsync(d_u, h_U, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (tbytes) SBP_CUDA(cudaMemcpyAsync(d_t, h_bc_table, tbytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = sbp_solve_ssprk53(ctx, op, static_cast<double*>(d_u), B, static_cast<const double*>(d_t), bc_row_stride, nsteps,
+                           h_steps, nullptr);
+    if (rc) return rc;
+    SBP_CUDA(cudaMemcpyAsync(h_U, d_u, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SBP_OK;
+}
+
+// ---- PCIe / host-memory copy ceiling of this box (what bounds the *_host entry points) ----------------------------------
+int32_t sbp_pcie_probe(sbp_ctx* ctx, size_t bytes, double* h2d_gbs, double* d2h_gbs, double* bidir_gbs) {
+    SBP_REQUIRE(ctx && bytes >= (1u << 20), SBP_EINVAL, "sbp_pcie_probe: need a ctx and at least 1 MiB");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    void *h_a = nullptr, *h_b = nullptr, *d_a = nullptr, *d_b = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    int32_t rc = SBP_OK;
+    auto fail = [&](const char* what) {
+        set_error("sbp_pcie_probe: %s failed: %s", what, cudaGetErrorString(cudaGetLastError()));
+        rc = SBP_ECUDA;
+    };
+    if (cudaHostAlloc(&h_a, bytes, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc(&h_b, bytes, cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc(&d_a, bytes) != cudaSuccess || cudaMalloc(&d_b, bytes) != cudaSuccess)
+        fail("allocation");
+    if (!rc) {
+        memset(h_a, 1, bytes), memset(h_b, 2, bytes);
+        cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventCreate(&e2);
+        auto timed = [&](bool up, bool down) {
+            double best = 0.0;
+            for (int rep = 0; rep < 3; rep++) {
+                cudaStreamSynchronize(ctx->s_in), cudaStreamSynchronize(ctx->s_out);
+                cudaEventRecord(e0, ctx->s_in);
+                cudaStreamWaitEvent(ctx->s_out, e0, 0);
+                if (up) cudaMemcpyAsync(d_a, h_a, bytes, cudaMemcpyHostToDevice, ctx->s_in);
+                if (down) cudaMemcpyAsync(h_b, d_b, bytes, cudaMemcpyDeviceToHost, ctx->s_out);
+                cudaEventRecord(e2, ctx->s_out);
+                cudaStreamWaitEvent(ctx->s_in, e2, 0);
+                cudaEventRecord(e1, ctx->s_in);
+                if (cudaEventSynchronize(e1) != cudaSuccess) return -1.0;
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                best = std::max(best, (double)bytes * ((up ? 1 : 0) + (down ? 1 : 0)) / (ms * 1e6));
+            }
+            return best;
+        };
+        const double u = timed(true, false), d = timed(false, true), b = timed(true, true);
+        if (u < 0 || d < 0 || b < 0) fail("timed copy");
+        if (h2d_gbs) *h2d_gbs = u;
+        if (d2h_gbs) *d2h_gbs = d;
+        if (bidir_gbs) *bidir_gbs = b;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (h_a) cudaFreeHost(h_a);
+    if (h_b) cudaFreeHost(h_b);
+    if (d_a) cudaFree(d_a);
+    if (d_b) cudaFree(d_b);
+    return rc;
 }
 
 }  // extern "C"

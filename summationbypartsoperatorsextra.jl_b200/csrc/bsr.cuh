@@ -25,6 +25,8 @@ struct BsrParams {
     double ca = 0.0, cb = 0.0, ch = 1.0;
     int fused = 0;
     int skew = 0;                     // bsr3.cu: start-up delay (cycles) of the second consumer warp of every scheduler
+    int pf = 0;                       // bsr3.cu: L2 prefetch distance of the box producer, in boxes of its stream (0: none)
+    int sem = 0;                      // bsr3.cu, 12 consumer warps: at most `sem` of the three warps of a scheduler multiply at a time (0: off)
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
     const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows
     const double* __restrict__ g;

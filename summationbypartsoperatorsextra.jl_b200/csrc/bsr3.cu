@@ -40,8 +40,8 @@
 #define SBP_B3_PING 0  // 1: the two consumer warps of a scheduler take turns on the tensor pipe (token through named barriers)
 #endif
 #ifndef SBP_B3_HELPER_FENCE
-#define SBP_B3_HELPER_FENCE 0  // 1: the proxy fence before a TMA store is executed by the helper thread that issues the store
-#endif
+#define SBP_B3_HELPER_FENCE 1  // 1: the proxy fence before a TMA store is executed by the helper thread that issues the store
+#endif                         // (after its acquire of the consumer warp's arrive; config 3: 0.2978 -> 0.2958 ms), 0: by the consumer warp
 #ifndef SBP_B3_DEFER
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
@@ -55,7 +55,10 @@ namespace sbp {
 #endif
 
 constexpr int kB3Stages = 4;      // box stages (mbarrier pairs)
-constexpr int kB3FragStages = 2;  // operator-fragment stages
+#ifndef SBP_B3_FSTAGES
+#define SBP_B3_FSTAGES 2
+#endif
+constexpr int kB3FragStages = SBP_B3_FSTAGES;  // operator-fragment stages
 
 // shared-memory loads at a 32-bit shared address + compile-time offset (volatile: they keep their place in the software pipeline)
 template <uint32_t OFF>
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     __shared__ uint64_t bar_full[kB3Stages], bar_empty[kB3Stages], fbar_full[kB3FragStages], fbar_empty[kB3FragStages];
     __shared__ uint64_t out_full[kBsrCH], out_empty[kBsrCH];  // HELP: staging buffer of consumer warp w filled / stored
     __shared__ uint64_t ext_full[kBsrCH];  // HELP + FUSED: the quads of `extra` for the warp's next block are in its staging buffer
+    __shared__ int sem_fin[4];  // CW == 12, p.sem: chains finished per scheduler (at most two of its three warps multiply at a time)
     // XT: the extra operand of a fused stage update travels through the staging buffers (TMA loads issued by the helpers)
     const bool XT = HELP && FUSED && p.cb != 0.0;
     static_assert(!HELP || (CW == kBsrCH && OUT == 2), "helper warps: 8 consumer warps with TMA output");
@@ -130,12 +134,35 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             mbar_init(&out_empty[s], 1);
             mbar_init(&ext_full[s], 1);
         }
+        for (int s = 0; s < 4; s++) sem_fin[s] = 0;
         mbar_fence_init();
     }
     __syncthreads();
 
     if (HELP && warp >= CONS + 2) {
         // ------- store helpers: per item and served consumer warp, wait for its staging buffer, store the two quads, hand it back -------
+#if SBP_B3_EXP == 11 || SBP_B3_EXP == 12
+        // what-if (WRONG RESULTS): one helper thread stores the staging area of all eight consumer warps as two {32 rows x TI}
+        // boxes (11) / four {16 x TI} boxes (12) per item instead of sixteen {4 x TI} boxes: same bytes, 1/8 (1/4) of the TMA rows
+        if (lane == 0 && warp == CONS + 2) {
+            int ph = 0;
+            constexpr int W = SBP_B3_EXP == 11 ? 32 : 16;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b0 = (int)(tile * TI);
+                for (int cc = 0; cc < p.nch; cc++) {
+                    for (int w = 0; w < kBsrCH; w++) mbar_wait(&out_full[w], ph);
+                    const int r = min(64 * cc, N - 64) & ~1;
+                    for (int k = 0; k < 64 / W; k++) tma_store_2d(&tmap_ex, r + W * k, b0, s_out + (size_t)k * W * TI);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                    for (int w = 0; w < kBsrCH; w++) mbar_arrive(&out_empty[w]);
+                    ph ^= 1;
+                }
+            }
+            bulk_wait<0>();
+        }
+        return;
+#endif
         if (lane == 0) {
             const int h = warp - (CONS + 2);
             int c = 0, ph = 0;
@@ -215,6 +242,15 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                                      : "memory");
                         if (SBP_B3_EXP == 3) jb = jn;
                         for (; jb < jn; jb++, x += BX) {
+                            if (p.pf > 0) {  // L2 prefetch of the box p.pf positions ahead in this CTA's box stream (HBM -> L2, no
+                                int jp = jb + p.pf;  // shared memory): the ring's lookahead is shallower than the HBM latency needs
+                                long long tp = tile;
+                                if (jp >= p.nbt) jp -= p.nbt, tp += gridDim.x;
+                                if (tp < ntiles)
+                                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(&tmap),
+                                                 "r"(jp * BX), "r"((int)(tp * TI))
+                                                 : "memory");
+                            }
                             const uint32_t dst = s_u32 + (uint32_t)slot * BOXB;
                             asm volatile(
                                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
@@ -328,6 +364,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
     constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0 && !HELP;
     int out_phase = 0, ext_phase = 0;
+    int sem_n = warp >> 2;  // CW == 12: index of this warp's next block among the blocks of its scheduler (rotation of three warps)
     double accs[DEFER ? 2 : 1][MT][2];
     int pv_rowA = 0, pv_rowB = 0, pv_b0 = 0, pv_state = 0;  // deferred block: rows of its quads, first tensor row, 1 = pending | 2 = scale | 4 = set
     // staging + TMA stores of one block's accumulators
@@ -412,6 +449,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         }
         mbar_wait(&bar_full[st], phase);
         if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
+        if (CW == 12 && p.sem) {  // block sem_n of this scheduler may multiply once sem_n - p.sem + 1... of its predecessors have finished
+            const uint32_t a = smem_u32(&sem_fin[warp & 3]);
+            int v;
+            do {
+                asm volatile("ld.volatile.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+            } while (v < sem_n - (p.sem - 1));
+        }
         // ---- DMMA chain, two fragments per trip: operands one fragment ahead, ring codes two ahead ----
         if (work) {
             double a0[MT], a1[MT];
@@ -447,6 +491,10 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
 
         const int nb = min(Bir - b0, TI);
         if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the other warp of this scheduler may start
+        if (CW == 12 && p.sem) {
+            if (lane == 0) atomicAdd(&sem_fin[warp & 3], 1);
+            sem_n += 3;
+        }
         // blocks that carry SAT terms finish their accumulators now (the terms read the ring); for the others a deferred
         // epilogue also takes over the scaling by alpha
         const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
@@ -652,6 +700,7 @@ static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     if (rc) return rc;
     CUtensorMap tmap_ex = tmap_out;  // fused stage update with an extra operand: its quads travel like the output's
     if (FUSED && HELP && p.extra && p.cb != 0.0) rc = make_tmap(&tmap_ex, p.extra, p.N, p.B, 4, TI);
+    if (SBP_B3_EXP == 11 || SBP_B3_EXP == 12) rc = make_tmap(&tmap_ex, p.dU, p.N, p.B, SBP_B3_EXP == 11 ? 32 : 16, TI);
     if (rc) return rc;
     SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (p.B + TI - 1) / TI;
@@ -735,6 +784,10 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
             skew = e ? atoi(e) : 0;
         }
         p.skew = skew;
+        const char* es = getenv("SBP_BSR_SEM");
+        p.sem = es ? atoi(es) : 0;
+        const char* ep = getenv("SBP_BSR_PF");
+        p.pf = std::min(ep ? atoi(ep) : 6, p.nbt - 1);  // measured (profiles/r2_bsr_notes.txt): 4-8 boxes ahead, config 3 0.312 -> 0.298 ms
     }
     static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
     if (verbose)

@@ -69,6 +69,9 @@ struct sbp_ctx {
     size_t pipe_bytes = 0;
     cudaEvent_t pipe_ev[2][3] = {};
     void* nccl_comm = nullptr;
+    // grow-only device buffers of the *_host / solve entry points: [0] boundary data, [1] Runge-Kutta work vectors, [2] state
+    void* aux[3] = {nullptr, nullptr, nullptr};
+    size_t aux_bytes[3] = {0, 0, 0};
 };
 
 struct sbp_op {

@@ -126,6 +126,12 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
     return v;
 }
+// coherent streaming load (evict-first): for operands that may alias memory the same kernel writes
+__device__ __forceinline__ double2 ldg_cs2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void stg_stream2(double* p, double x, double y) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};\n" ::"l"(p), "d"(x), "d"(y) : "memory");
 }

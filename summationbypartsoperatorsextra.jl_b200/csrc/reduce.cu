@@ -19,7 +19,7 @@ __device__ __forceinline__ double group_sum(double v) {
 template <int GS, int MODE>
 __global__ void __launch_bounds__(256) k_integrate(const double* __restrict__ U, const double* __restrict__ V,
                                                    const double* __restrict__ w, int N, int G, long long B,
-                                                   double* __restrict__ out, double* __restrict__ partial) {
+                                                   double* __restrict__ out, double* __restrict__ partial, int power) {
     __shared__ double warp_part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (GS - 1);
@@ -40,7 +40,16 @@ __global__ void __launch_bounds__(256) k_integrate(const double* __restrict__ U,
                 double f;
                 if (MODE == 0) f = ui;
                 else if (MODE == 1) f = ui * ui;
-                else f = ui * ldg_stream1(V + b * N + i);
+                else if (MODE == 2) f = ui * ldg_stream1(V + b * N + i);
+                else if (MODE == 3) f = fabs(ui);
+                else {  // u^k, k >= 0 (binary powering: the rounding of Base.power_by_squaring, which x -> x^k calls)
+                    f = 1.0;
+                    double x = ui;
+                    for (int k = power; k > 0; k >>= 1) {
+                        if (k & 1) f *= x;
+                        x *= x;
+                    }
+                }
                 s = fma(wg[i], f, s);
             }
         }
@@ -92,9 +101,11 @@ template <int GS>
 static int32_t launch_integrate_gs(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V,
                                    long long B, int mode, double* out, double* partial, int grid) {
     switch (mode) {
-        case 0: k_integrate<GS, 0><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial); break;
-        case 1: k_integrate<GS, 1><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial); break;
-        default: k_integrate<GS, 2><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial); break;
+        case 0: k_integrate<GS, 0><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial, 0); break;
+        case 1: k_integrate<GS, 1><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial, 0); break;
+        case 2: k_integrate<GS, 2><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial, 0); break;
+        case 3: k_integrate<GS, 3><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial, 0); break;
+        default: k_integrate<GS, 4><<<grid, 256, 0, ctx->stream>>>(U, V, d_w, N, G, B, out, partial, mode - 16); break;
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
@@ -103,7 +114,8 @@ static int32_t launch_integrate_gs(sbp_ctx* ctx, const double* d_w, int N, int G
 
 int32_t launch_integrate(sbp_ctx* ctx, const double* d_w, int N, int G, const double* U, const double* V, int64_t B,
                          int mode, double* out, double* out_sum) {
-    SBP_REQUIRE(mode >= 0 && mode <= 2, SBP_EINVAL, "integrate: mode must be 0, 1 or 2");
+    SBP_REQUIRE((mode >= 0 && mode <= 3) || (mode >= 16 && mode < 16 + 64), SBP_EINVAL,
+                "integrate: mode must be 0 (u), 1 (u^2), 2 (u*v), 3 (|u|) or 16 + k (u^k, 0 <= k < 64)");
     SBP_REQUIRE(mode != 2 || V != nullptr, SBP_EINVAL, "integrate: mode 2 needs V");
     const int gs = pick_gs(N);
     const long long groups_per_block = 256 / gs;
@@ -151,27 +163,29 @@ int32_t launch_scale(sbp_ctx* ctx, const double* d_w, int N, double* U, int64_t 
 // ---- Y = a X + b Y + c Z + d W ------------------------------------------------------------------------
 // Stage updates of the explicit Runge-Kutta schemes in ONE pass (SSPRK53's u3 = a30 u + a32 u2 + b32 h f(u2) reads three
 // vectors and writes one).  Y is read only when b != 0 (it may be uninitialised memory otherwise); Z, W may be NULL.
+// Y may alias X, Z or W (sbp_rhs_advection*_stage allows Uextra == Unext; DeviceBatch.axpby_/lincomb_ accept self as an
+// operand): no __restrict__, and coherent streaming loads (ld.global.cs) -- a non-coherent (.nc) load of memory the same
+// kernel writes is undefined.  Every thread reads all of its operands before it writes its element.
 template <bool VEC>
-__global__ void __launch_bounds__(256) k_lincomb(double* __restrict__ Y, const double* __restrict__ X,
-                                                 const double* __restrict__ Z, const double* __restrict__ W,
+__global__ void __launch_bounds__(256) k_lincomb(double* Y, const double* X, const double* Z, const double* W,
                                                  long long n, double a, double b, double c, double d) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (VEC) {
         const long long n2 = n / 2;
         for (long long i = i0; i < n2; i += stride) {
-            const double2 x = ldg_stream2(X + 2 * i);
+            const double2 x = ldg_cs2(X + 2 * i);
             double2 y = make_double2(a * x.x, a * x.y);
             if (b != 0.0) {
                 const double2 o = reinterpret_cast<const double2*>(Y)[i];
                 y.x = fma(b, o.x, y.x), y.y = fma(b, o.y, y.y);
             }
             if (Z) {
-                const double2 z = ldg_stream2(Z + 2 * i);
+                const double2 z = ldg_cs2(Z + 2 * i);
                 y.x = fma(c, z.x, y.x), y.y = fma(c, z.y, y.y);
             }
             if (W) {
-                const double2 w = ldg_stream2(W + 2 * i);
+                const double2 w = ldg_cs2(W + 2 * i);
                 y.x = fma(d, w.x, y.x), y.y = fma(d, w.y, y.y);
             }
             reinterpret_cast<double2*>(Y)[i] = y;

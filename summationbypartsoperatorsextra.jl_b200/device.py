@@ -123,6 +123,12 @@ class Context:
             pass
         return cur
 
+    def pcie_probe(self, nbytes: int = 256 << 20) -> dict:
+        """Pinned-memory copy rates of this box in GB/s: {"h2d", "d2h", "bidir"} (`sbp_pcie_probe`)."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        check(self._lib.sbp_pcie_probe(self.handle, int(nbytes), C.byref(a), C.byref(b), C.byref(c)))
+        return {"h2d": a.value, "d2h": b.value, "bidir": c.value}
+
     def pinned_empty(self, shape) -> np.ndarray:
         """Page-locked host array (for the end-to-end host-buffer path); release with `free_pinned`."""
         n = int(np.prod(shape))

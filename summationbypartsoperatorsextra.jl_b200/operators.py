@@ -37,7 +37,19 @@ def abs2(x):
     return x * x
 
 
-_INTEGRATE_MODES = {identity: 0, abs2: 1, np.square: 1, None: 0}
+class power:
+    """`x -> x^k` for an integer 0 <= k < 64 as an `integrate` integrand (evaluated on the device by binary powering)."""
+
+    def __init__(self, k: int):
+        if int(k) != k or not 0 <= int(k) < 64:
+            raise ArgumentError("power(k): integer 0 <= k < 64")
+        self.k = int(k)
+
+    def __call__(self, x):
+        return x ** self.k
+
+
+_INTEGRATE_MODES = {identity: 0, abs2: 1, np.square: 1, None: 0, abs: 3, np.abs: 3, np.absolute: 3}
 
 
 def _ptr(x):
@@ -142,8 +154,8 @@ class DerivativeOperator:
     `_scale()` (constant folded into every apply), `weights()` and `grid`."""
 
     storage = "auto"  # "auto" | "dense" | "sparse"
-    # sbp_op_dense_create flags: 0 = use the even/odd kernel iff D is bitwise centro-antisymmetric;
-    # _lib.DENSE_NO_SYMMETRY never; _lib.DENSE_SYMMETRIZE also when it is so up to 256 eps (uses (D - JDJ)/2)
+    # sbp_op_dense_create flags: 0 = use the even/odd kernel when D is centro-antisymmetric up to 256 eps (the
+    # antisymmetric part (D - JDJ)/2 is applied); _lib.DENSE_NO_SYMMETRY never; _lib.DENSE_SYM_BITWISE only when bitwise
     dense_flags = _lib.DENSE_AUTO
 
     def __init__(self):
@@ -252,7 +264,8 @@ def Matrix(D):
 
 def integrate(func, u: DeviceBatch, D: DerivativeOperator, v: DeviceBatch | None = None, total: bool = False):
     """`integrate(func, u, D)` = sum_i func(u_i) w_i per instance (host array of B values; a float for B == 1).
-    func is `identity`, `abs2`/`np.square`, or None with `v` given (weighted inner product sum_i w_i u_i v_i).
+    func is `identity`, `abs2`/`np.square`, `abs`, `power(k)`, or None with `v` given (weighted inner product
+    sum_i w_i u_i v_i).
     `total=True` additionally returns the sum over the batch computed on the device."""
     if u.N != D.size(1):
         raise DimensionMismatch("sizes of input vector and operator do not match")
@@ -262,9 +275,13 @@ def integrate(func, u: DeviceBatch, D: DerivativeOperator, v: DeviceBatch | None
         if v.shape != u.shape:
             raise DimensionMismatch("u and v differ in shape")
     else:
-        if func not in _INTEGRATE_MODES:
-            raise ArgumentError("device integrate supports identity, abs2 and the weighted inner product")
-        mode = _INTEGRATE_MODES[func]
+        if isinstance(func, power):
+            mode = 16 + func.k
+        elif func in _INTEGRATE_MODES:
+            mode = _INTEGRATE_MODES[func]
+        else:
+            raise ArgumentError("device integrate supports identity, abs2, abs, power(k) and the weighted inner product "
+                                "(the reference accepts any func, src/subcell_operators.jl:92-94)")
     op = D.device_op(ctx)
     out = RawBuffer(ctx, max(u.B, 1) * 8 + 8)
     check(ctx._lib.sbp_integrate(ctx.handle, op.handle, _ptr(u.ptr), _ptr(v.ptr) if v is not None else None, u.B,
@@ -313,10 +330,8 @@ class NodalBasis:
         D = (lam[None, :] / lam[:, None]) / diff
         np.fill_diagonal(D, 0.0)
         np.fill_diagonal(D, -D.sum(axis=1))
-        if np.array_equal(x, -x[::-1]):
-            # node set symmetric about 0 => the exact derivative matrix is centro-antisymmetric; impose it exactly
-            # (removes the O(eps) asymmetry of the barycentric products and lets the device use the even/odd kernel)
-            D = 0.5 * (D - D[::-1, ::-1])
+        # (kept exactly as the barycentric formula yields it, like PolynomialBases.jl: for symmetric node sets it is
+        # centro-antisymmetric only up to rounding; the library detects that at upload, sbp_b200.h SBP_DENSE_*)
         self.D = D
 
     def interpolation_matrix(self, dest) -> np.ndarray:
