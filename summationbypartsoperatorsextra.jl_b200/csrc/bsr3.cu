@@ -328,8 +328,6 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     };
     Rec r0 = load_rec(kBsrCH * pc + ps);
     advance();
-    Rec r1 = load_rec(kBsrCH * pc + ps);
-    advance();
     int skip = warp / kBsrCH, myslot = warp % kBsrCH;  // items to pass before this warp's next block; its slot there
     double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0;
     if (SAT == 2) {
@@ -391,7 +389,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
      for (int hf = 0; hf < (DEFER ? 2 : 1); hf++) {
       if (tile >= ntlr) goto done;
       if (CW == kBsrCH || skip == 0) {
-        const Rec r2 = load_rec(kBsrCH * pc + ps);  // record of the block after the next one
+        const Rec r1 = load_rec(kBsrCH * pc + ps);
         advance();
         const int nf = r0.a.y;
         const bool active = r0.a.z < Nr;  // padding records of the last chunk carry rows >= N and no fragments
@@ -643,7 +641,6 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
         r0 = r1;
-        r1 = r2;
         skip = (myslot + CW) / kBsrCH - 1;
         myslot = (myslot + CW) & (kBsrCH - 1);
       } else {
@@ -748,7 +745,10 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const char* ev = getenv("SBP_BSR_V3");
     const int enabled = ev ? atoi(ev) : -1;
     if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
-    if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N))) return false;
+    // (r2: also plain applies of operators whose tile row is much longer than the ring -- 2D clouds: config 3's A without the
+    // SAT terms 0.322 ms on k_bsr, 0.280 here)
+    const bool wide = p.nbt > 2 * op->bsr_nbox[1];
+    if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N || wide))) return false;
     // (read at every launch: the tests switch them)
     const char* ecw = getenv("SBP_BSR_CW");
     const int forced_cw = ecw ? atoi(ecw) : 8;
@@ -787,7 +787,9 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
         const char* es = getenv("SBP_BSR_SEM");
         p.sem = es ? atoi(es) : 0;
         const char* ep = getenv("SBP_BSR_PF");
-        p.pf = std::min(ep ? atoi(ep) : 6, p.nbt - 1);  // measured (profiles/r2_bsr_notes.txt): 4-8 boxes ahead, config 3 0.312 -> 0.298 ms
+        // default: 5 boxes ahead when a tile row is much longer than the ring (2D clouds: config 3 0.312 -> 0.291 ms, N = 900 / 1936
+        // -5 / -4 %); banded 1D operators, whose ring holds most of the row, lose 6-13 % with any prefetch (profiles/r2_bsr_notes.txt)
+        p.pf = std::min(ep ? atoi(ep) : (p.nbt > 2 * p.nbox ? 5 : 0), p.nbt - 1);
     }
     static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
     if (verbose)

@@ -79,8 +79,8 @@ def main():
 
         def step(i):
             S._lib.check(lib.sbp_apply(h, op.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, 1.0, 0.0))
-    elif args.workload in ("config3", "config1b"):
-        if args.workload == "config3":  # 2D MFSBP advection RHS with SAT on a jittered 36x36 cloud
+    elif args.workload in ("config3", "config1b", "config3apply"):
+        if args.workload in ("config3", "config3apply"):  # 2D MFSBP advection RHS with SAT on a jittered 36x36 cloud
             n1 = args.n if args.n != 64 else 36  # --n: grid points per direction (N = n1^2), batch scaled to ~85 M DOF
             B = 65536 if n1 == 36 else (65536 * 1296 // (n1 * n1)) // 64 * 64
             rng = np.random.default_rng(0)
@@ -120,6 +120,12 @@ def main():
 
         def step(i):
             semi(du, u, None, 0.1)
+
+        if args.workload == "config3apply":  # the same operator without the SAT terms: mul!(du, A, u, -1)
+            inner = semi._dev[id(ctx)][1]
+
+            def step(i):
+                S._lib.check(lib.sbp_apply(h, inner.handle, C.c_void_p(Y.data_ptr()), C.c_void_p(U.data_ptr()), B, -1.0, 0.0))
     else:
         raise SystemExit("unknown workload")
     for i in range(5):
