@@ -45,6 +45,8 @@ def load():
         dp, ip, L, I, D = C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_double
         lib.oracle_max_threads.restype = I
         lib.oracle_apply_dense.argtypes = [dp, I, dp, dp, L, D, D, I]
+        lib.oracle_apply_dense_blas.argtypes = [dp, dp, I, dp, dp, L, D, D, I]
+        lib.oracle_apply_dense_blas.restype = None
         lib.oracle_apply_subcell.argtypes = [dp, dp, dp, I, I, ip, dp, dp, dp, L, D, D, I]
         lib.oracle_apply_csr.argtypes = [ip, ip, dp, I, dp, dp, L, D, D, I]
         lib.oracle_rhs_advection2d.argtypes = [dp, ip, ip, dp, I, dp, ip, dp, L, dp, dp, L, I, I]
@@ -71,6 +73,29 @@ def apply_dense(Dmat, U, alpha=1.0, beta=0.0, Y=None, nthreads=1):
     B, N = U.shape
     Y = np.empty_like(U) if Y is None else Y
     load().oracle_apply_dense(_p(D), N, _p(U), _p(Y), B, alpha, beta, nthreads)
+    return Y
+
+
+def openblas_dgemv_address() -> int:
+    """Address of the Fortran-interface `dgemv_` of the OpenBLAS bundled with scipy (scipy.linalg.cython_blas exports the
+    BLAS entry points as PyCapsules) -- the routine Julia's `mul!(dest, D::Matrix, u, alpha, beta)` ends up in."""
+    from scipy.linalg import cython_blas
+
+    cap = cython_blas.__pyx_capi__["dgemv"]
+    C.pythonapi.PyCapsule_GetName.restype = C.c_char_p
+    C.pythonapi.PyCapsule_GetName.argtypes = [C.py_object]
+    C.pythonapi.PyCapsule_GetPointer.restype = C.c_void_p
+    C.pythonapi.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    return C.pythonapi.PyCapsule_GetPointer(cap, C.pythonapi.PyCapsule_GetName(cap))
+
+
+def apply_dense_blas(Dmat, U, alpha=1.0, beta=0.0, Y=None, nthreads=1):
+    """per-instance OpenBLAS dgemv loop (the reference's own BLAS call per vector), instances spread over OpenMP threads."""
+    D = np.asfortranarray(Dmat, dtype=np.float64)
+    U = np.ascontiguousarray(U, dtype=np.float64)
+    B, N = U.shape
+    Y = np.empty_like(U) if Y is None else Y
+    load().oracle_apply_dense_blas(C.c_void_p(openblas_dgemv_address()), _p(D), N, _p(U), _p(Y), B, alpha, beta, nthreads)
     return Y
 
 

@@ -10,6 +10,7 @@
  *   oracle_apply_dense      LinearAlgebra.mul!(dest, D::Matrix, u, alpha, beta) -> BLAS dgemv('N') on a column-major
  *                           matrix (src/polynomialbases_operators.jl:148, src/subcell_operators.jl:279, upstream
  *                           MatrixDerivativeOperator); axpy-ordered loop = the dgemv_n algorithm
+ *   oracle_apply_dense_blas the same per-instance loop calling OpenBLAS dgemv_ itself (what Julia's mul! dispatches to)
  *   oracle_apply_subcell    src/subcell_operators.jl:270-280 INCLUDING the per-call rebuild
  *                           D = inv(Diagonal(w)) * (Q_left + Q_right) (:183-186) that the reference performs
  *   oracle_rhs_advection2d  src/conservation_laws/multidimensional_linear_advection.jl:60-81 INCLUDING the per-call
@@ -54,6 +55,23 @@ void oracle_apply_dense(const double* D, int N, const double* U, double* Y, long
 #pragma omp for schedule(static)
         for (long b = 0; b < B; b++) gemv_n(N, alpha, D, U + b * N, beta, Y + b * N, tmp);
         free(tmp);
+    }
+}
+
+/* The same loop through the BLAS the reference itself calls: `mul!(dest, D::Matrix, u, alpha, beta)` is LinearAlgebra's
+ * BLAS.gemv!('N', alpha, D, u, beta, dest) = OpenBLAS dgemv_ (Fortran interface).  `dgemv` is the address of that symbol in
+ * the OpenBLAS that numpy / scipy bundle here (taken from scipy.linalg.cython_blas by oracle/c_oracle.py). */
+typedef void (*dgemv_fn)(char* trans, int* m, int* n, double* alpha, double* a, int* lda, double* x, int* incx, double* beta,
+                         double* y, int* incy);
+void oracle_apply_dense_blas(void* dgemv, const double* D, int N, const double* U, double* Y, long B, double alpha,
+                             double beta, int nthreads) {
+    dgemv_fn f = (dgemv_fn)dgemv;
+#pragma omp parallel for schedule(static) num_threads(nthreads > 0 ? nthreads : 1)
+    for (long b = 0; b < B; b++) {
+        char tr = 'N';
+        int n = N, one = 1;
+        double a = alpha, be = beta;
+        f(&tr, &n, &n, &a, (double*)D, &n, (double*)(U + b * N), &one, &be, Y + b * N, &one);
     }
 }
 
