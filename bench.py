@@ -516,7 +516,7 @@ def pcie_and_e2e(torch, S, ctx, dist, rank, world, op, N, B, steps):
 
     # host buffers and the copy-issuing thread on the GPU's NUMA node (restored below: the CPU baseline uses every core)
     affinity0 = os.sched_getaffinity(0)
-    e2e_cpus = ctx.bind_host_to_gpu_numa()
+    e2e_cpus = sorted(affinity0) if os.environ.get("SBP_BENCH_NO_BIND") else ctx.bind_host_to_gpu_numa()
     barrier()
     probe = ctx.pcie_probe(256 << 20)
     hU, hY = ctx.pinned_empty((B, N)), ctx.pinned_empty((B, N))
@@ -534,8 +534,11 @@ def pcie_and_e2e(torch, S, ctx, dist, rank, world, op, N, B, steps):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=torch.device("cuda", ctx.device))
+    per_rank = [te.clone() for _ in range(world)]
     if dist is not None:
+        dist.all_gather(per_rank, te)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    per_rank_s = [float(x.item()) for x in per_rank]
     e2e_s = float(te.item())
     checksum = float(hY[:: max(1, B // 1024)].sum())
     ctx.free_pinned(hU), ctx.free_pinned(hY)
@@ -549,7 +552,7 @@ def pcie_and_e2e(torch, S, ctx, dist, rank, world, op, N, B, steps):
     return {"value": dofs * steps / e2e_s / 1e9, "unit": "GDOF/s", "h2d_bytes_per_step": int(8 * N * B),
             "d2h_bytes_per_step": int(8 * N * B), "steps": steps,
             "api": "sbp_apply_host (pinned host buffers, chunked H2D/compute/D2H overlap)", "host_numa_cpus": len(e2e_cpus),
-            "checksum": checksum,
+            "checksum": checksum, "per_rank_seconds": per_rank_s,
             "pcie_probe_gbs": {"h2d": pr[0], "d2h": pr[1], "bidir_sum": pr[2],
                                "how": "sbp_pcie_probe: pinned cudaMemcpyAsync of 256 MiB, alone and both directions at once, "
                                       f"all {world} rank(s) at the same time, summed over ranks"},

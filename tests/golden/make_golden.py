@@ -6,7 +6,12 @@ which is pinned to the reference's own known-answer tests by tests/test_oracle.p
 tests/golden/reference_known_answers.json).  The fixture freezes those outputs: the oracle (CPU suite) and the CUDA
 path (GPU suite) are both compared against the stored arrays, so neither can drift silently.
 
-    python tests/golden/make_golden.py        # rewrites hotpath_golden.npz (deterministic)
+    python tests/golden/make_golden.py        # rewrites hotpath_golden.npz and hotpath_inputs.bin (deterministic)
+
+`hotpath_inputs.bin` holds the seeded INPUT vectors in a flat container (tests/golden/golden_io.py) that
+`baseline/julia_oracle.jl` reads on a Julia machine to produce `hotpath_golden_julia.bin`: the same outputs from the real
+reference (`mul!`, `semi(du, u, p, t)`, `analyze_quantities`).  tests/test_julia_golden.py compares the oracle and the CUDA
+path with that file when it is present (until then those tests are skipped and parity stays "unpinned" for the RHS rows).
 """
 import os
 import sys
@@ -66,7 +71,18 @@ def build():
     return out
 
 
+INPUT_KEYS = ("lgl16_U", "lgl16_Y0", "mn4_20_U", "mn4_21_U", "subcell_U", "adv2d_U", "adv1d_U")
+
+
 if __name__ == "__main__":
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hotpath_golden.npz")
-    np.savez_compressed(path, **build())
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "hotpath_golden.npz")
+    arrays = build()
+    np.savez_compressed(path, **arrays)
     print("wrote", path, os.path.getsize(path), "bytes")
+    # the INPUT vectors in the flat container that baseline/julia_oracle.jl reads (numpy's RNG does not exist in Julia)
+    sys.path.insert(0, here)
+    from golden_io import write_bin
+
+    write_bin(os.path.join(here, "hotpath_inputs.bin"), {k: arrays[k] for k in INPUT_KEYS})
+    print("wrote hotpath_inputs.bin")
