@@ -403,6 +403,62 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
         del U, Y
     except Exception as e:  # pragma: no cover
         out["config1_batched_banded_N101_rhs1d"] = {"error": str(e)[:200]}
+    try:  # config 1, the reference's own CPU-runnable case: the WHOLE solve of examples/RBF_FSBP_advection.jl (N = 101 banded
+        # operator, SSPRK53, dt = 0.009, tspan = (0, 0.5): 56 steps x 5 stages) for 1 / 64 / 1024 instances, wall clock
+        from oracle import c_oracle as CO
+        from oracle import sbp_oracle as O
+
+        N = 101
+        D1 = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        D1.storage = "sparse"
+        u0f = lambda x: np.tanh(50 * (x - 0.1))
+        lbc, rbc = (lambda t: float(u0f(0.0 - t))), (lambda t: 0.0)
+        semi1 = S.VariableLinearAdvectionNonperiodicSemidiscretization(D1, None, lambda x: 1.0, False, lbc, rbc)
+        cs = (0.0, 0.377268915331368, 0.754537830662736, 0.728985661612188, 0.699226135931670)
+        sched, t = [], 0.0
+        while t < 0.5 - 1e-14:
+            hh = min(0.009, 0.5 - t)
+            sched.append((t, hh))
+            t += hh
+        table = np.ascontiguousarray([[lbc(tt + c * hh), rbc(tt + c * hh)] for tt, hh in sched for c in cs])
+        hs = np.ascontiguousarray([hh for _, hh in sched])
+        opb = semi1.device_op(ctx)
+        tab = ctx.upload_array(table)
+        Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        w = Do.weights()
+        u0 = u0f(Do.grid)
+        CO.solve_ssprk53_1d(Do.matrix(), np.ones(N), w[0], w[-1], u0, hs, table)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            CO.solve_ssprk53_1d(Do.matrix(), np.ones(N), w[0], w[-1], u0, hs, table)
+        cpu_ms = (time.perf_counter() - t0) / 10 * 1e3
+        res = {"steps": len(sched), "stages": 5 * len(sched), "N": N,
+               "cpu_port_ms_per_solve_one_core": cpu_ms,
+               "cpu_port": "oracle_solve_ssprk53_1d: dense dgemv per stage as the reference's operator type does, one core"}
+        for Bs in (1, 64, 1024):
+            u = ctx.upload(np.tile(u0, (Bs, 1)))
+            row = {}
+            for force, name in (("1", "single_launch"), ("0", "launch_per_stage")):
+                os.environ["SBP_SOLVE_SMALL"] = force
+                ts = []
+                for rep in range(4):
+                    u.copy_from_host(np.tile(u0, (Bs, 1)))
+                    n0 = ctx.launch_count
+                    t0 = time.perf_counter()
+                    S._lib.check(ctx._lib.sbp_solve_ssprk53(ctx.handle, opb.handle, C.c_void_p(u.ptr), Bs, C.c_void_p(tab.ptr),
+                                                            2, len(sched), hs.ctypes.data_as(C.c_void_p), None))
+                    ctx.synchronize()
+                    ts.append((time.perf_counter() - t0) * 1e3)
+                row[name + "_ms"] = float(np.median(ts[1:]))
+                row[name + "_launches"] = int(ctx.launch_count - n0)
+            os.environ.pop("SBP_SOLVE_SMALL", None)
+            row["cpu_port_ms_all_cores"] = cpu_ms * -(-Bs // host_threads())
+            row["speedup_vs_cpu_port"] = row["cpu_port_ms_all_cores"] / row["single_launch_ms"]
+            res[f"B{Bs}"] = row
+        tab.free()
+        out["config1_whole_solve_latency"] = res
+    except Exception as e:  # pragma: no cover
+        out["config1_whole_solve_latency"] = {"error": str(e)[:300]}
     try:  # config 5 (reduced batch): dense N = 4096 operator, B = 8192 -> DMMA DGEMM
         N, B = 4096, 8192
         rng = np.random.default_rng(0)

@@ -51,6 +51,8 @@ def load():
         lib.oracle_apply_csr.argtypes = [ip, ip, dp, I, dp, dp, L, D, D, I]
         lib.oracle_rhs_advection2d.argtypes = [dp, ip, ip, dp, I, dp, ip, dp, L, dp, dp, L, I, I]
         lib.oracle_energy.argtypes = [dp, I, I, dp, dp, L, I]
+        lib.oracle_solve_ssprk53_1d.argtypes = [dp, I, dp, D, D, dp, L, dp, dp, dp]
+        lib.oracle_solve_ssprk53_1d.restype = None
         for f in ("oracle_apply_dense", "oracle_apply_subcell", "oracle_apply_csr", "oracle_rhs_advection2d",
                   "oracle_energy"):
             getattr(lib, f).restype = None
@@ -157,3 +159,17 @@ def energy(w, U, nthreads=1):
     E = np.empty(B)
     load().oracle_energy(_p(W), N, W.shape[0], _p(U), _p(E), B, nthreads)
     return E
+
+
+def solve_ssprk53_1d(Dmat, a, w0, wN, u0, hsteps, bc_table):
+    """Whole fixed-step SSPRK53 solve of the upstream 1D semidiscretization for one instance (the CPU path of
+    examples/RBF_FSBP_advection.jl: dense dgemv per stage); bc_table: (5 * nsteps, 2) [left, right] at the stage times."""
+    D = np.asfortranarray(Dmat, dtype=np.float64)
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    u = np.array(u0, dtype=np.float64, copy=True)
+    hs = np.ascontiguousarray(hsteps, dtype=np.float64)
+    bc = np.ascontiguousarray(bc_table, dtype=np.float64)
+    N = len(u)
+    work = np.empty(5 * N)
+    load().oracle_solve_ssprk53_1d(_p(D), N, _p(a), float(w0), float(wN), _p(u), len(hs), _p(hs), _p(bc), _p(work))
+    return u

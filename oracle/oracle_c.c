@@ -161,3 +161,40 @@ void oracle_energy(const double* w, int N, int G, const double* U, double* energ
         energy[b] = e;
     }
 }
+
+/* Whole fixed-step SSPRK53 solve of the upstream 1D semidiscretization for ONE instance, as examples/RBF_FSBP_advection.jl
+ * runs it on the CPU (BASELINE config 1): per stage du = -D (a .* u) through the dense dgemv the reference's operator type
+ * performs (MatrixDerivativeOperator mul! on the dense-stored D), Godunov SATs at both ends, then the Shu-Osher combination.
+ * bc: (5 * nsteps) rows [left, right] at the stage times; u (N) in/out; work: 5 * N doubles. */
+static void rhs1d(int N, const double* restrict D, const double* restrict a, double w0, double wN, const double* restrict u,
+                  const double* bc, double* restrict du, double* restrict au, double* restrict tmp) {
+    for (int i = 0; i < N; i++) au[i] = a[i] * u[i];
+    gemv_n(N, -1.0, D, au, 0.0, du, tmp);
+    const double fl = a[0] > 0.0 ? a[0] * bc[0] : a[0] * u[0];
+    const double fr = a[N - 1] > 0.0 ? a[N - 1] * u[N - 1] : a[N - 1] * bc[1];
+    du[0] += (fl - a[0] * u[0]) / w0;
+    du[N - 1] -= (fr - a[N - 1] * u[N - 1]) / wN;
+}
+void oracle_solve_ssprk53_1d(const double* D, int N, const double* a, double w0, double wN, double* u, long nsteps,
+                             const double* hsteps, const double* bc, double* work) {
+    const double a30 = 0.355909775063327, a32 = 0.644090224936674, a40 = 0.367933791638137, a43 = 0.632066208361863,
+                 a52 = 0.237593836598569, a54 = 0.762406163401431, b10 = 0.377268915331368, b21 = 0.377268915331368,
+                 b32 = 0.242995220537396, b43 = 0.238458932846290, b54 = 0.287632146308408;
+    double *u1 = work, *u2 = work + N, *u3 = work + 2 * N, *du = work + 3 * N, *au = work + 4 * N;
+    double* tmp = (double*)malloc(sizeof(double) * (size_t)N);
+    for (long s = 0; s < nsteps; s++) {
+        const double h = hsteps[s];
+        const double* b = bc + 10 * s;
+        rhs1d(N, D, a, w0, wN, u, b, du, au, tmp);
+        for (int i = 0; i < N; i++) u1[i] = u[i] + b10 * h * du[i];
+        rhs1d(N, D, a, w0, wN, u1, b + 2, du, au, tmp);
+        for (int i = 0; i < N; i++) u2[i] = u1[i] + b21 * h * du[i];
+        rhs1d(N, D, a, w0, wN, u2, b + 4, du, au, tmp);
+        for (int i = 0; i < N; i++) u3[i] = a30 * u[i] + a32 * u2[i] + b32 * h * du[i];
+        rhs1d(N, D, a, w0, wN, u3, b + 6, du, au, tmp);
+        for (int i = 0; i < N; i++) u1[i] = a40 * u[i] + a43 * u3[i] + b43 * h * du[i];
+        rhs1d(N, D, a, w0, wN, u1, b + 8, du, au, tmp);
+        for (int i = 0; i < N; i++) u[i] = a52 * u2[i] + a54 * u1[i] + b54 * h * du[i];
+    }
+    free(tmp);
+}

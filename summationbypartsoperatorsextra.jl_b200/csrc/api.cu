@@ -837,7 +837,7 @@ int32_t sbp_op_destroy(sbp_op* op) {
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
                     op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
-                    op->d_rb_bdiag,  op->d_bsr_item, op->d_bsr_pos3};
+                    op->d_rb_bdiag,  op->d_bsr_item, op->d_bsr_pos3, op->d_csr_rowptr, op->d_csr_col, op->d_csr_val};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -896,6 +896,10 @@ int32_t sbp_op_sparse_create(sbp_ctx* ctx, int32_t N, const int32_t* h_rowptr, c
     std::vector<double> val(h_val, h_val + nnz);
     int32_t rc = build_sell(op, N, rp, col, val);
     if (!rc) rc = build_bsr(op, N, rp, col, val);
+    if (!rc) rc = upload(&op->d_csr_rowptr, rp);
+    if (!rc) rc = upload(&op->d_csr_col, col);
+    if (!rc) rc = upload(&op->d_csr_val, val);
+    for (int r = 0; r < N; r++) op->csr_max_row = std::max(op->csr_max_row, rp[r + 1] - rp[r]);
     if (!rc) {
         // kernel choice (SBP_SPARSE_KERNEL=sell|bsr overrides): the tensor-core kernel whenever a tile fits in smem
         const char* e = getenv("SBP_SPARSE_KERNEL");
@@ -1398,6 +1402,20 @@ int32_t sbp_solve_ssprk53(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, 
     const bool two_d = op->kind == SBP_OP_ADVECTION2D;
     SBP_REQUIRE(bc_row_stride >= (two_d ? op->N : 2), SBP_EDIM, "bc_row_stride too small (%lld)", (long long)bc_row_stride);
     SBP_CUDA(cudaSetDevice(ctx->device));
+    // small batches: the whole solve in ONE launch (a CTA per instance, state in shared memory; solve_small.cu) instead of
+    // 5 launches per step.  SBP_SOLVE_SMALL=0 forces the batched path, =1 the single launch whenever it is applicable.
+    {
+        const char* e = getenv("SBP_SOLVE_SMALL");  // (once per solve, not per launch)
+        const int force = e ? atoi(e) : -1;
+        const bool applicable = solve_small_applies(ctx, op, force == 1 ? 1 : B);
+        if (force != 0 && applicable) {
+            void* d_h = nullptr;
+            int32_t rc = ensure_aux(ctx, 3, (size_t)nsteps * sizeof(double), &d_h);
+            if (rc) return rc;
+            SBP_CUDA(cudaMemcpyAsync(d_h, h_steps, (size_t)nsteps * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            return launch_solve_small(ctx, op, U, B, bc_table, bc_row_stride, nsteps, static_cast<const double*>(d_h));
+        }
+    }
     const size_t n = (size_t)B * op->N;
     if (!work) {
         void* w = nullptr;

@@ -70,8 +70,9 @@ struct sbp_ctx {
     cudaEvent_t pipe_ev[2][3] = {};
     void* nccl_comm = nullptr;
     // grow-only device buffers of the *_host / solve entry points: [0] boundary data, [1] Runge-Kutta work vectors, [2] state
-    void* aux[3] = {nullptr, nullptr, nullptr};
-    size_t aux_bytes[3] = {0, 0, 0};
+    // [3] step sizes of the single-launch solve
+    void* aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t aux_bytes[4] = {0, 0, 0, 0};
 };
 
 struct sbp_op {
@@ -106,6 +107,11 @@ struct sbp_op {
     int* d_sell_col = nullptr;
     double* d_sell_val = nullptr;
     int max_row_nnz = 0;
+    // plain CSR copy (row-wise consumers: the single-launch solve of small batches, solve_small.cu)
+    int* d_csr_rowptr = nullptr;
+    int* d_csr_col = nullptr;
+    double* d_csr_val = nullptr;
+    int csr_max_row = 0;  // most non-zeros of a row
     // sparse, block-sparse DMMA image (bsr.cu): row blocks of 8 rows, fragments of 4 gathered columns
     double* d_bsr_val = nullptr;  // [fragment][32] B-operand fragments (row g, column t)
     int* d_bsr_pos = nullptr;     // [fragment][4] (box - boxlo[chunk]) << 8 | column % kBsrBX
@@ -205,4 +211,8 @@ int32_t launch_adv2d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const
 int32_t launch_adv1d(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B, const double* bc,
                      int64_t bc_stride, double* quantities);
 int32_t ensure_scratch(sbp_ctx* ctx, size_t doubles);
+// solve_small.cu: a whole SSPRK53 solve of a small batch in one launch (one CTA per instance, state in shared memory)
+bool solve_small_applies(const sbp_ctx* ctx, const sbp_op* op, int64_t B);
+int32_t launch_solve_small(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const double* bc_table,
+                           int64_t bc_row_stride, int64_t nsteps, const double* d_hsteps);
 }  // namespace sbp

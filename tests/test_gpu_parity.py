@@ -673,6 +673,58 @@ def test_solve_ssprk53_host_and_pcie_probe(ctx):
     assert rates["h2d"] > 1.0 and rates["d2h"] > 1.0 and rates["bidir"] >= 0.9 * max(rates["h2d"], rates["d2h"])
 
 
+@pytest.mark.parametrize("case", ["1d_sparse", "1d_dense", "1d_variable_speed", "2d_sparse", "2d_dense"])
+@pytest.mark.parametrize("B", [1, 5, 64])
+def test_solve_ssprk53_single_launch(ctx, case, B, monkeypatch):
+    """Small batches: the whole fixed-step SSPRK53 solve runs in ONE launch (k_solve_ssprk53_small: a CTA per instance, state
+    in shared memory) instead of five launches per step.  Checked against the oracle's SSPRK53 on the same operator and against
+    the batched path (SBP_SOLVE_SMALL=0) -- config 1 of BASELINE (examples/RBF_FSBP_advection.jl) at B = 1 is this path."""
+    cs = (0.0, 0.377268915331368, 0.754537830662736, 0.728985661612188, 0.699226135931670)
+    nsteps, dt = 9, 0.004
+    if case.startswith("1d"):
+        N = 101
+        D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        D.storage = "dense" if case == "1d_dense" else "sparse"
+        Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        afun = (lambda x: 1.0 + 0.3 * np.sin(2 * x)) if case == "1d_variable_speed" else (lambda x: 1.0)
+        lbc, rbc = (lambda t: np.tanh(50 * (-t - 0.1))), (lambda t: 0.2 * np.cos(t))
+        semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, afun, False, lbc, rbc)
+        semio = O.AdvectionSemi1D(Do, afun, lbc, rbc)
+        rhs = semio.rhs
+        table = np.array([[lbc(s * dt + c * dt), rbc(s * dt + c * dt)] for s in range(nsteps) for c in cs])
+    else:
+        Dm = _scattered_mfsbp(10, seed=4)
+        a = (1.0, 0.6)
+        g = lambda x, t: np.exp(-30 * ((x[0] - a[0] * t) ** 2 + (x[1] - a[1] * t) ** 2)) + 0.1 * np.sin(3 * x[0] - x[1] + t)
+        semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(Dm, a, g, storage=case[3:])
+        semio = O.AdvectionSemi2D(_oracle_md(Dm), a, g, Dm.corners)
+        rhs = semio.rhs
+        N = Dm.N
+        table = np.stack([semi.boundary_values(s * dt + c * dt) for s in range(nsteps) for c in cs])
+    U0 = rand_batch(B, N, 77)
+    hs = np.full(nsteps, dt)
+    op = semi.device_op(ctx)
+    tab = ctx.upload_array(np.ascontiguousarray(table))
+    res = {}
+    for force in ("1", "0"):
+        monkeypatch.setenv("SBP_SOLVE_SMALL", force)
+        u = ctx.upload(U0)
+        n0 = ctx.launch_count
+        S._lib.check(ctx._lib.sbp_solve_ssprk53(ctx.handle, op.handle, C.c_void_p(u.ptr), B, C.c_void_p(tab.ptr),
+                                                table.shape[1], nsteps, hs.ctypes.data_as(C.c_void_p), None))
+        res[force] = (u.to_host(), ctx.launch_count - n0)
+    assert res["1"][1] == 1 and res["0"][1] >= 5 * nsteps  # one launch against five (or more) per step
+    ref = U0.copy()
+    for b in range(B):
+        v = U0[b]
+        for s in range(nsteps):
+            v = O.ssprk53_step(rhs, v, s * dt, dt)
+        ref[b] = v
+    assert rel_err(res["1"][0], ref) <= 1e-11 and rel_err(res["0"][0], ref) <= 1e-11
+    assert rel_err(res["1"][0], res["0"][0]) <= 1e-12
+    tab.free()
+
+
 # ---- full-size configurations through size-independent properties ---------------------------------------------------
 def test_config2_full_size_properties(ctx):
     """BASELINE config 2 at full size (N = 64, B = 2^20): instances are tiled copies of 2048 distinct vectors, so the

@@ -355,3 +355,29 @@ def test_oracle_reproduces_golden_fixture():
     assert sorted(new) == sorted(old.files)
     for k in old.files:
         assert np.allclose(new[k], old[k], rtol=1e-14, atol=1e-14), k
+
+
+def test_c_port_whole_solve_matches_numpy_oracle():
+    """oracle_solve_ssprk53_1d (the CPU leg of the config-1 solve timing) reproduces the numpy oracle's SSPRK53 run of
+    examples/RBF_FSBP_advection.jl (N = 101, dt = 0.009, tspan = (0, 0.5): 56 steps)."""
+    from oracle import c_oracle as CO
+
+    N = 101
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    u0f = lambda x: np.tanh(50 * (x - 0.1))
+    lbc, rbc = (lambda t: u0f(0.0 - t)), (lambda t: 0.0)
+    semio = O.AdvectionSemi1D(Do, lambda x: 1.0, lbc, rbc)
+    cs = (0.0, 0.377268915331368, 0.754537830662736, 0.728985661612188, 0.699226135931670)
+    steps, t = [], 0.0
+    while t < 0.5 - 1e-14:
+        h = min(0.009, 0.5 - t)
+        steps.append((t, h))
+        t += h
+    assert len(steps) == 56
+    table = np.array([[lbc(tt + c * hh), rbc(tt + c * hh)] for tt, hh in steps for c in cs])
+    w = Do.weights()
+    uc = CO.solve_ssprk53_1d(Do.matrix(), np.ones(N), w[0], w[-1], u0f(Do.grid), [h for _, h in steps], table)
+    v = u0f(Do.grid)
+    for tt, hh in steps:
+        v = O.ssprk53_step(semio.rhs, v, tt, hh)
+    assert np.max(np.abs(uc - v)) <= 1e-13
