@@ -241,6 +241,41 @@ int32_t sbp_comm_destroy(sbp_ctx* ctx);
 int32_t sbp_solve_ssprk53(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const double* bc_table,
                           int64_t bc_row_stride, int64_t nsteps, const double* h_steps, double* work);
 
+/* Low-storage 3S*+ Runge-Kutta schemes with embedded error estimator and FSAL (Ranocha, Dalcin, Parsani, Ketcheson 2021):
+ * the family of RDPK3SpFSAL49, the integrator of examples/RBF_MFSBP_advection.jl:21-27.  The scheme is passed as a tableau
+ * (the coefficients of RDPK3SpFSAL49 live in OrdinaryDiffEqLowStorageRK; the Julia shim extracts them from the algorithm's
+ * cache): one step is  tmp = uprev; u = tmp + beta[0] dt k1; for i = 1..s-1: k = f(u, t + c[i-1] dt); tmp += delta[i-1] u;
+ * u = gamma1[i-1] u + gamma2[i-1] tmp + gamma3[i-1] uprev + beta[i] dt k;  error estimate utilde = dt (sum_i bhat[i] k_i +
+ * bhat_fsal f(u_new)). */
+typedef struct {
+    int32_t stages;               /* s                                                                    */
+    int32_t order_for_controller; /* k = min(order, embedded order) + 1: exponent divisor of the PID controller */
+    const double* gamma1;         /* s - 1 entries each (stages 2..s): gamma1, gamma2, gamma3, delta, c    */
+    const double* gamma2;
+    const double* gamma3;
+    const double* delta;
+    const double* c;
+    const double* beta;           /* s entries                                                             */
+    const double* bhat;           /* s entries (weights of the error estimate)                              */
+    double bhat_fsal;
+} sbp_tableau_3sp;
+/* boundary data at time t into h_row (host; N doubles for a 2D bundle: g per node, 2 doubles [left, right] for a 1D bundle) */
+typedef void (*sbp_bc_fn)(double t, double* h_row, void* user);
+/* called (stream synchronised, U holds u(t)) whenever the integration lands on a stop time */
+typedef void (*sbp_stop_fn)(double t, void* user);
+/* Integrate U (device, B*N) from t0 to t1.  adaptive != 0: step size control as OrdinaryDiffEq's PIDController(pid[0..2]) with
+ * EEst = rms(utilde / (abstol + max(|uprev|, |u|) reltol)) over the whole batch (one dt for all instances), accept when the
+ * limited factor 1 + atan(q - 1) >= 0.81; adaptive == 0: fixed steps dt0.  Steps are clipped to land on tstops (sorted; the
+ * tstops of an AnalysisCallback(semi; dt = ...)) and on t1.  h_stats (may be NULL): [accepted, rejected, last dt]. */
+int32_t sbp_solve_3sp_fsal(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const sbp_tableau_3sp* tab, double t0,
+                           double t1, double dt0, int32_t adaptive, double abstol, double reltol, const double* pid,
+                           sbp_bc_fn bc, void* bc_user, const double* tstops, int32_t n_tstops, sbp_stop_fn on_stop,
+                           void* stop_user, int64_t max_steps, double* h_stats);
+/* rms_i( utilde_i / (abstol + max(|uprev_i|, |u_i|) reltol) ) over n device doubles -> *h_rms (host; synchronises): the error
+ * norm of OrdinaryDiffEq's calculate_residuals + ODE_DEFAULT_NORM, deterministic two-pass reduction. */
+int32_t sbp_error_norm(sbp_ctx* ctx, const double* utilde, const double* uprev, const double* u, int64_t n, double abstol,
+                       double reltol, double* h_rms);
+
 /* ---- host-buffer entry points (end-to-end path: pinned staging + chunked H2D/compute/D2H overlap) ------- */
 /* h_dU = alpha*scale*D*h_U + beta*h_dU for host arrays; copies are pipelined in chunks of
  * `chunk_instances` (0 = auto) over three streams.  This is what `mul!(dU::Matrix, D, U::Matrix)` on

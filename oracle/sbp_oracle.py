@@ -722,3 +722,56 @@ def ssprk53_step(rhs, u, t, dt):
     u4 = a40 * u + a43 * u3 + b43 * dt * rhs(u3, t + c3 * dt)
     u5 = a52 * u2 + a54 * u4 + b54 * dt * rhs(u4, t + c4 * dt)
     return u5
+
+
+def solve_lowstorage_3sp(rhs, u0, t0, t1, dt0, tab, adaptive=True, abstol=1e-6, reltol=1e-3, pid=(0.38, 0.18, 0.01), tstops=()):
+    """Low-storage 3S*+ FSAL Runge-Kutta integration with embedded error estimate and PID step size control, restating
+    OrdinaryDiffEqLowStorageRK's LowStorageRK3SpFSAL perform_step + OrdinaryDiffEq's PIDController (third-party, version
+    unpinned: the integrator of examples/RBF_MFSBP_advection.jl:21-27 is RDPK3SpFSAL49 of that family).  `tab`: object with
+    gamma1, gamma2, gamma3, delta, c (stages 2..s), beta, bhat (stages 1..s), bhat_fsal, order, embedded_order.
+    Returns (u, accepted, rejected, list of accepted times)."""
+    u = np.array(u0, dtype=np.float64, copy=True)
+    s = len(tab.beta)
+    k_ctrl = min(tab.order, tab.embedded_order) + 1
+    err = [1.0, 1.0, 1.0]
+    t, dt = float(t0), float(dt0)
+    stops = [x for x in tstops if t0 < x < t1]
+    nxt, nacc, nrej, times = 0, 0, 0, []
+    kf = rhs(u, t)
+    teps = 1e-12 * max(1.0, abs(t1))
+    while t < t1 - teps:
+        target, h, clipped = (stops[nxt] if nxt < len(stops) else t1), dt, False
+        if t + h >= target - teps:
+            h, clipped = target - t, True
+        uprev, tmp = u.copy(), u.copy()
+        un = tmp + tab.beta[0] * h * kf
+        ut = tab.bhat[0] * h * kf
+        for i in range(1, s):
+            k = rhs(un, t + tab.c[i - 1] * h)
+            tmp = tmp + tab.delta[i - 1] * un
+            un = tab.gamma1[i - 1] * un + tab.gamma2[i - 1] * tmp + tab.gamma3[i - 1] * uprev + tab.beta[i] * h * k
+            ut = ut + tab.bhat[i] * h * k
+        kl = rhs(un, t + h)
+        accept, q = True, 1.0
+        if adaptive:
+            ut = ut + tab.bhat_fsal * h * kl
+            r = ut / (abstol + np.maximum(np.abs(uprev), np.abs(un)) * reltol)
+            eest = max(np.sqrt(np.mean(r * r)), np.finfo(float).eps)
+            err[0] = 1.0 / eest
+            q = err[0] ** (pid[0] / k_ctrl) * err[1] ** (pid[1] / k_ctrl) * err[2] ** (pid[2] / k_ctrl)
+            q = 1.0 + np.arctan(q - 1.0)
+            accept = q >= 0.81
+        if accept:
+            t = target if clipped else t + h
+            u, kf = un, kl
+            nacc += 1
+            times.append(t)
+            if adaptive:
+                err[2], err[1] = err[1], err[0]
+            dt = h * q if adaptive else dt0
+            if clipped and nxt < len(stops) and target == stops[nxt]:
+                nxt += 1
+        else:
+            nrej += 1
+            dt = h * q
+    return u, nacc, nrej, times

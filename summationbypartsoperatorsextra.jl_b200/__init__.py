@@ -20,9 +20,11 @@ from .operators import (DerivativeOperator, GaussLegendre, GaussRadauLeft, Gauss
                         neighborhood_sparsity_pattern, polynomialbases_derivative_operator, power,
                         scale_by_inverse_mass_matrix_, scale_by_mass_matrix_, tensor_product_operator_2D,
                         upload_csr, upload_dense, upload_sparse, upload_table)
-from .conservation_laws import (AnalysisCallback, MultidimensionalLinearAdvectionNonperiodicSemidiscretization,
+from .conservation_laws import (AnalysisCallback, LowStorage3SpTableau,
+                                MultidimensionalLinearAdvectionNonperiodicSemidiscretization,
                                 ODEProblem, VariableLinearAdvectionNonperiodicSemidiscretization,
-                                analyze_quantities, quantities, semidiscretize, solve_ssprk53, tstops)
+                                analyze_quantities, quantities, semidiscretize, solve_lowstorage_3sp,
+                                solve_ssprk53, step_schedule, tstops)
 from .container import load_operator, save_operator
 from .sharding import shard_range
 

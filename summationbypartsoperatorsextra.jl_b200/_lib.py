@@ -105,7 +105,21 @@ SIGNATURES = {
     "sbp_solve_ssprk53": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_void_p]),
     "sbp_solve_ssprk53_host": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_void_p]),
     "sbp_pcie_probe": (c_i32, [c_void_p, c_size_t, P(c_dbl), P(c_dbl), P(c_dbl)]),
+    "sbp_solve_3sp_fsal": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_dbl, c_dbl, c_dbl, c_i32, c_dbl, c_dbl,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i64, c_void_p]),
+    "sbp_error_norm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, P(c_dbl)]),
 }
+
+
+class Tableau3Sp(C.Structure):
+    """`sbp_tableau_3sp` of include/sbp_b200.h."""
+    _fields_ = [("stages", c_i32), ("order_for_controller", c_i32), ("gamma1", c_void_p), ("gamma2", c_void_p),
+                ("gamma3", c_void_p), ("delta", c_void_p), ("c", c_void_p), ("beta", c_void_p), ("bhat", c_void_p),
+                ("bhat_fsal", c_dbl)]
+
+
+BC_FN = C.CFUNCTYPE(None, c_dbl, P(c_dbl), c_void_p)
+STOP_FN = C.CFUNCTYPE(None, c_dbl, c_void_p)
 
 
 def build(verbose: bool = False) -> str:

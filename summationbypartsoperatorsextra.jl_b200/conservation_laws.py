@@ -439,3 +439,112 @@ def solve_ssprk53(prob: ODEProblem, dt: float, callback: AnalysisCallback | None
         if callback is not None and callback.should_fire(si + 1, tn, si + 1 == len(steps)):
             callback(du, u, p, tn)
     return u
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# low-storage 3S*+ schemes with embedded error estimator and FSAL (the family of RDPK3SpFSAL49)
+# ------------------------------------------------------------------------------------------------------------------
+class LowStorage3SpTableau:
+    """Coefficients of a 3S*+ FSAL scheme in OrdinaryDiffEqLowStorageRK's layout (`LowStorageRK3SpFSALConstantCache`):
+    gamma1/gamma2/gamma3/delta/c for stages 2..s, beta and bhat for stages 1..s, bhat_fsal; `order` and `embedded_order`
+    set the exponent divisor k = min(order, embedded_order) + 1 of the PID controller.
+
+    RDPK3SpFSAL49 itself (examples/RBF_MFSBP_advection.jl:24) is NOT tabulated here: its 9-stage coefficients are the result
+    of a numerical optimisation and live in OrdinaryDiffEqLowStorageRK, which is neither under /root/reference nor in this
+    image.  `SBPB200.export_tableau(path, RDPK3SpFSAL49())` writes them on a Julia machine; `LowStorage3SpTableau.load(path)`
+    reads that file.  The classical schemes below are written in the same form and are what the tests integrate with."""
+
+    def __init__(self, gamma1, gamma2, gamma3, delta, c, beta, bhat, bhat_fsal, order, embedded_order, name=""):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.gamma1, self.gamma2, self.gamma3, self.delta, self.c = f(gamma1), f(gamma2), f(gamma3), f(delta), f(c)
+        self.beta, self.bhat, self.bhat_fsal = f(beta), f(bhat), float(bhat_fsal)
+        self.order, self.embedded_order, self.name = int(order), int(embedded_order), name
+        s = len(self.beta)
+        if len(self.bhat) != s or any(len(a) != s - 1 for a in (self.gamma1, self.gamma2, self.gamma3, self.delta, self.c)):
+            raise ArgumentError("inconsistent tableau lengths")
+
+    stages = property(lambda self: len(self.beta))
+
+    @classmethod
+    def load(cls, path):
+        """Flat binary tableau written by `SBPB200.export_tableau` (SBPGOLD1 container, tests/golden/golden_io.py layout)."""
+        import struct
+
+        out = {}
+        with open(path, "rb") as fh:
+            if fh.read(8) != b"SBPGOLD1":
+                raise ArgumentError(f"{path}: not a tableau file")
+            (count,) = struct.unpack("<q", fh.read(8))
+            for _ in range(count):
+                (ln,) = struct.unpack("<q", fh.read(8))
+                name = fh.read(ln).decode()
+                (nd,) = struct.unpack("<q", fh.read(8))
+                shape = struct.unpack(f"<{nd}q", fh.read(8 * nd)) if nd else ()
+                n = int(np.prod(shape)) if nd else 1
+                out[name] = np.frombuffer(fh.read(8 * n), dtype="<f8").copy()
+        return cls(out["gamma1"], out["gamma2"], out["gamma3"], out["delta"], out["c"], out["beta"], out["bhat"],
+                   float(out["bhat_fsal"][0]), int(out["order"][0]), int(out["embedded_order"][0]), name=path)
+
+    @classmethod
+    def ssprk33_heun(cls):
+        """SSPRK33 (Shu-Osher) in 3S* form (gamma2 = delta = 0: S3 = uprev carries the convex combinations) with the embedded
+        second-order weights (1/2, 1/2, 0): error weights b - bhat = (-1/3, -1/3, 2/3)."""
+        return cls([0.25, 2.0 / 3.0], [0.0, 0.0], [0.75, 1.0 / 3.0], [0.0, 0.0], [1.0, 0.5], [1.0, 0.25, 2.0 / 3.0],
+                   [-1.0 / 3.0, -1.0 / 3.0, 2.0 / 3.0], 0.0, 3, 2, name="SSPRK33 / Heun pair in 3S*+ form")
+
+    @classmethod
+    def heun_euler(cls):
+        """Heun's method with the embedded Euler step (error weights (-1/2, 1/2)), in 3S* form."""
+        return cls([0.5], [0.0], [0.5], [0.0], [1.0], [1.0, 0.5], [-0.5, 0.5], 0.0, 2, 1, name="Heun / Euler pair in 3S*+ form")
+
+
+def solve_lowstorage_3sp(prob: ODEProblem, tableau: LowStorage3SpTableau, dt: float, adaptive: bool = True,
+                         abstol: float = 1e-6, reltol: float = 1e-3, pid=(0.38, 0.18, 0.01),
+                         callback: AnalysisCallback | None = None, max_steps: int = 1_000_000):
+    """`solve(ode, alg; dt, abstol, reltol, callback)` for a 3S*+ FSAL low-storage scheme (alg = RDPK3SpFSAL49() in
+    examples/RBF_MFSBP_advection.jl:21-27), device resident: the time loop, the five-vector stage updates, the embedded error
+    norm and OrdinaryDiffEq's PID step size controller run inside the library (`sbp_solve_3sp_fsal`); the host evaluates the
+    boundary function when the library asks for it and records the analysis callback at its stop times.
+    Returns (u(t_end), {"naccept", "nreject", "dt_last"}).  `pid` defaults to the controller OrdinaryDiffEq attaches to
+    RDPK3SpFSAL49; defaults of abstol / reltol are OrdinaryDiffEq's."""
+    semi, p = prob.f, prob.p
+    u: DeviceBatch = prob.u0.copy()
+    ctx = u.ctx
+    t0, tend = float(prob.tspan[0]), float(prob.tspan[1])
+    op = semi.device_op(ctx)
+    two_d = isinstance(semi, MultidimensionalLinearAdvectionNonperiodicSemidiscretization)
+    row = semi.derivative.N if two_d else 2
+
+    def bc_cb(t, h_row, _user):
+        vals = semi.boundary_values(t) if two_d else (semi.left_bc(t), semi.right_bc(t))
+        for i in range(row):
+            h_row[i] = vals[i]
+
+    if two_d:  # bulk copy instead of the element loop
+        def bc_cb(t, h_row, _user):  # noqa: F811
+            C.memmove(h_row, _as_f64(semi.boundary_values(t)).ctypes.data, 8 * row)
+
+    du = u.similar() if callback is not None else None
+    stops = np.ascontiguousarray(callback.stop_times(t0, tend) if callback is not None else [], dtype=np.float64)
+
+    def stop_cb(t, _user):
+        if callback is not None and callback.should_fire(-1, t, False):
+            callback(du, u, p, t)
+
+    tab = _lib.Tableau3Sp(tableau.stages, min(tableau.order, tableau.embedded_order) + 1,
+                          tableau.gamma1.ctypes.data, tableau.gamma2.ctypes.data, tableau.gamma3.ctypes.data,
+                          tableau.delta.ctypes.data, tableau.c.ctypes.data, tableau.beta.ctypes.data,
+                          tableau.bhat.ctypes.data, tableau.bhat_fsal)
+    pid_a = np.ascontiguousarray(pid, dtype=np.float64)
+    stats = np.zeros(3)
+    bc_f, stop_f = _lib.BC_FN(bc_cb), _lib.STOP_FN(stop_cb)
+    if callback is not None and callback.should_fire(0, t0, False):
+        callback(du, u, p, t0)
+    check(ctx._lib.sbp_solve_3sp_fsal(ctx.handle, op.handle, _ptr(u.ptr), u.B, C.byref(tab), t0, tend, float(dt),
+                                      1 if adaptive else 0, float(abstol), float(reltol), pid_a.ctypes.data_as(C.c_void_p),
+                                      C.cast(bc_f, C.c_void_p), None, stops.ctypes.data_as(C.c_void_p), len(stops),
+                                      C.cast(stop_f, C.c_void_p), None, int(max_steps), stats.ctypes.data_as(C.c_void_p)))
+    ctx.synchronize()
+    if callback is not None and callback.should_fire(-1, tend, True):
+        callback(du, u, p, tend)
+    return u, {"naccept": int(stats[0]), "nreject": int(stats[1]), "dt_last": float(stats[2])}

@@ -658,7 +658,7 @@ static int32_t host_pipeline(sbp_ctx* ctx, int N, int G, double* h_out, const do
 }
 
 // grow-only device buffer owned by the ctx (boundary data / work vectors of the *_host and solve entry points)
-static int32_t ensure_aux(sbp_ctx* ctx, int slot, size_t bytes, void** out) {
+int32_t ensure_aux(sbp_ctx* ctx, int slot, size_t bytes, void** out) {
     if (ctx->aux_bytes[slot] < bytes) {
         SBP_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->aux[slot]) cudaFree(ctx->aux[slot]);

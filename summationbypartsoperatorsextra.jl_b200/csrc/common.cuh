@@ -211,6 +211,7 @@ int32_t launch_adv2d_epilogue(sbp_ctx* ctx, const sbp_op* adv, double* dU, const
 int32_t launch_adv1d(sbp_ctx* ctx, const sbp_op* adv, double* dU, const double* U, int64_t B, const double* bc,
                      int64_t bc_stride, double* quantities);
 int32_t ensure_scratch(sbp_ctx* ctx, size_t doubles);
+int32_t ensure_aux(sbp_ctx* ctx, int slot, size_t bytes, void** out);  // grow-only device buffer sbp_ctx::aux[slot]
 // solve_small.cu: a whole SSPRK53 solve of a small batch in one launch (one CTA per instance, state in shared memory)
 bool solve_small_applies(const sbp_ctx* ctx, const sbp_op* op, int64_t B);
 int32_t launch_solve_small(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, const double* bc_table,

@@ -550,6 +550,37 @@ function solve_ssprk53!(u::DeviceBatch, semi, tspan; dt::Real, callback = nothin
     return u
 end
 
+# ---- low-storage 3S*+ FSAL schemes (RDPK3SpFSAL49 of examples/RBF_MFSBP_advection.jl:24) -------------------------------------
+"""
+    export_tableau(path, cache; order, embedded_order)
+
+Write the coefficients of a 3S*+ FSAL low-storage scheme in the flat `SBPGOLD1` container that
+`sbp_b200.LowStorage3SpTableau.load` and `sbp_solve_3sp_fsal` take.  `cache` is the constant cache of the algorithm in
+OrdinaryDiffEqLowStorageRK, e.g. `OrdinaryDiffEqLowStorageRK.RDPK3SpFSAL49ConstantCache(Float64, Float64)` with
+`order = 4, embedded_order = 3` (field names `γ12end, γ22end, γ32end, δ2end, β1, β2end, c2end, bhat1, bhat2end, bhatfsal` of
+`LowStorageRK3SpFSALConstantCache`; the package is third party and absent from the build image, so check them against the
+installed version).
+"""
+function export_tableau(path::AbstractString, cache; order::Integer, embedded_order::Integer)
+    arrays = ["gamma1" => collect(Float64, cache.γ12end), "gamma2" => collect(Float64, cache.γ22end),
+              "gamma3" => collect(Float64, cache.γ32end), "delta" => collect(Float64, cache.δ2end),
+              "c" => collect(Float64, cache.c2end), "beta" => vcat(Float64(cache.β1), collect(Float64, cache.β2end)),
+              "bhat" => vcat(Float64(cache.bhat1), collect(Float64, cache.bhat2end)), "bhat_fsal" => [Float64(cache.bhatfsal)],
+              "order" => [Float64(order)], "embedded_order" => [Float64(embedded_order)]]
+    open(path, "w") do io
+        write(io, codeunits("SBPGOLD1"))
+        write(io, Int64(length(arrays)))
+        for (name, a) in arrays
+            write(io, Int64(ncodeunits(name)))
+            write(io, codeunits(name))
+            write(io, Int64(1))
+            write(io, Int64(length(a)))
+            write(io, a)
+        end
+    end
+    return path
+end
+
 # ---- portable operator container (replaces the `.jls` files of examples/RBF_MFSBP.jl:51-52) ---------------------------
 # Flat little-endian binary file, layout documented in ../container.py (`SBPOP001`); read by `sbp_b200.load_operator`.
 #   D = multidimensional_function_space_operator(...)        # built once on the CPU (Optim), as in the reference

@@ -725,6 +725,57 @@ def test_solve_ssprk53_single_launch(ctx, case, B, monkeypatch):
     tab.free()
 
 
+@pytest.mark.parametrize("kind", ["1d", "2d"])
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_solve_lowstorage_3sp_fsal(ctx, kind, adaptive):
+    """Low-storage 3S*+ FSAL integration with embedded error estimate and PID step size control (the scheme family of
+    RDPK3SpFSAL49, examples/RBF_MFSBP_advection.jl:21-27) inside the library (sbp_solve_3sp_fsal) against the oracle's
+    restatement of the same algorithm on the same tableau: identical accept / reject history and final state."""
+    tab = S.LowStorage3SpTableau.ssprk33_heun()
+    if kind == "1d":
+        N = 61
+        D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        D.storage = "sparse"
+        Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+        u0f = lambda x: np.exp(-100 * (x - 0.3) ** 2)
+        lbc, rbc = (lambda t: np.exp(-100 * (-t - 0.3) ** 2)), (lambda t: 0.0)
+        semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, lambda x: 1.0, False, lbc, rbc)
+        semio = O.AdvectionSemi1D(Do, lambda x: 1.0, lbc, rbc)
+        grid = Do.grid
+        u0 = u0f(grid)
+    else:
+        Dm = _scattered_mfsbp(10, seed=6)
+        a = (1.0, 0.5)
+        uex = lambda x, t: np.exp(-20 * ((x[0] - a[0] * t + 0.3) ** 2 + (x[1] - a[1] * t + 0.2) ** 2))
+        semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(Dm, a, uex)
+        semio = O.AdvectionSemi2D(_oracle_md(Dm), a, uex, Dm.corners)
+        u0 = np.array([uex(x, 0.0) for x in Dm.grid])
+    B, tend, dt0 = 3, 0.2, 2e-3
+    prob = S.ODEProblem(semi, ctx.upload(np.tile(u0, (B, 1))), (0.0, tend))
+    cb = S.AnalysisCallback(semi, dt=0.05)
+    u, st = S.solve_lowstorage_3sp(prob, tab, dt0, adaptive=adaptive, abstol=1e-7, reltol=1e-5, callback=cb)
+    # the oracle integrates ONE instance; the batch norm equals the single-instance norm because all instances are equal
+    uo, nacc, nrej, times = O.solve_lowstorage_3sp(semio.rhs, u0, 0.0, tend, dt0, tab, adaptive=adaptive, abstol=1e-7,
+                                                    reltol=1e-5, tstops=[0.05, 0.1, 0.15])
+    assert (st["naccept"], st["nreject"]) == (nacc, nrej)
+    assert rel_err(u.to_host(), np.tile(uo, (B, 1))) <= 1e-10
+    assert np.allclose(S.tstops(cb), [0.0, 0.05, 0.1, 0.15, 0.2], rtol=0, atol=1e-12)
+    if adaptive:
+        assert st["dt_last"] != dt0  # the controller moved the step size
+
+
+def test_error_norm_reduction(ctx):
+    n = 100003
+    rng = np.random.default_rng(5)
+    ut, up, u = rng.normal(size=n) * 1e-4, rng.normal(size=n), rng.normal(size=n)
+    a, b, c = ctx.upload(ut), ctx.upload(up), ctx.upload(u)
+    out = C.c_double()
+    S._lib.check(ctx._lib.sbp_error_norm(ctx.handle, C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(c.ptr), n, 1e-6, 1e-3,
+                                         C.byref(out)))
+    r = ut / (1e-6 + np.maximum(np.abs(up), np.abs(u)) * 1e-3)
+    assert abs(out.value - np.sqrt(np.mean(r * r))) <= 1e-13 * out.value
+
+
 # ---- full-size configurations through size-independent properties ---------------------------------------------------
 def test_config2_full_size_properties(ctx):
     """BASELINE config 2 at full size (N = 64, B = 2^20): instances are tiled copies of 2048 distinct vectors, so the

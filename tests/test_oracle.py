@@ -381,3 +381,24 @@ def test_c_port_whole_solve_matches_numpy_oracle():
     for tt, hh in steps:
         v = O.ssprk53_step(semio.rhs, v, tt, hh)
     assert np.max(np.abs(uc - v)) <= 1e-13
+
+
+def test_lowstorage_3sp_scheme_order_and_controller():
+    """The oracle's restatement of the 3S*+ FSAL step (the scheme family of RDPK3SpFSAL49) with the SSPRK33 / Heun tableau in
+    that form: third order in fixed-step mode, and the PID-controlled run meets its tolerance on a problem with a known
+    solution (u' = -lambda u + sin t)."""
+    import sbp_b200 as S
+
+    tab = S.LowStorage3SpTableau.ssprk33_heun()
+    lam = np.array([1.0, 2.0])
+    rhs = lambda u, t: -lam * u + np.sin(t)
+    exact = lambda t: (1 + 1 / (lam**2 + 1)) * np.exp(-lam * t) + (lam * np.sin(t) - np.cos(t)) / (lam**2 + 1)
+    errs = []
+    for dt in (0.1, 0.05, 0.025):
+        u, nacc, nrej, _ = O.solve_lowstorage_3sp(rhs, np.ones(2), 0.0, 1.0, dt, tab, adaptive=False)
+        assert nrej == 0 and nacc == round(1.0 / dt)
+        errs.append(np.max(np.abs(u - exact(1.0))))
+    assert 2.8 < np.log2(errs[0] / errs[1]) < 3.3 and 2.8 < np.log2(errs[1] / errs[2]) < 3.3
+    u, nacc, nrej, times = O.solve_lowstorage_3sp(rhs, np.ones(2), 0.0, 1.0, 0.01, tab, adaptive=True, abstol=1e-8, reltol=1e-6,
+                                                  tstops=[0.25, 0.5])
+    assert np.max(np.abs(u - exact(1.0))) < 1e-6 and 0.25 in times and 0.5 in times and abs(times[-1] - 1.0) < 1e-12
