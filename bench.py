@@ -439,7 +439,7 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
             u = ctx.upload(np.tile(u0, (Bs, 1)))
             row = {}
             for force, name in (("1", "single_launch"), ("0", "launch_per_stage")):
-                os.environ["SBP_SOLVE_SMALL"] = force
+                ctx.set_option("solve_small", int(force))
                 ts = []
                 for rep in range(4):
                     u.copy_from_host(np.tile(u0, (Bs, 1)))
@@ -451,7 +451,7 @@ def extra_workloads(torch, S, ctx, hbm_peak, steps=6):
                     ts.append((time.perf_counter() - t0) * 1e3)
                 row[name + "_ms"] = float(np.median(ts[1:]))
                 row[name + "_launches"] = int(ctx.launch_count - n0)
-            os.environ.pop("SBP_SOLVE_SMALL", None)
+            ctx.set_option("solve_small", -1)
             row["cpu_port_ms_all_cores"] = cpu_ms * -(-Bs // host_threads())
             row["speedup_vs_cpu_port"] = row["cpu_port_ms_all_cores"] / row["single_launch_ms"]
             res[f"B{Bs}"] = row

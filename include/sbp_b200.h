@@ -88,6 +88,12 @@ int64_t sbp_ctx_launch_count(sbp_ctx* ctx);
  * buffers and threads on the GPU's NUMA node (/sys/bus/pci/devices/<id>/local_cpulist) before calling the *_host entry points */
 int32_t sbp_ctx_pci_bus_id(sbp_ctx* ctx, char* buf, int32_t len);
 
+/* Tuning / debugging options of a context ("bsr_v3", "bsr_pf", "solve_small", "sparse_kernel", ...: the table in
+ * csrc/common.cuh, enum Tune).  Every option takes its default from its SBP_* environment variable ONCE, when the context is
+ * created; no launch path reads the environment. */
+int32_t sbp_ctx_set_option(sbp_ctx* ctx, const char* name, int32_t value);
+int32_t sbp_ctx_get_option(sbp_ctx* ctx, const char* name, int32_t* value);
+
 /* ---- memory ---------------------------------------------------------------------------- */
 int32_t sbp_malloc(sbp_ctx* ctx, size_t bytes, void** dptr);
 int32_t sbp_free(sbp_ctx* ctx, void* dptr);

@@ -66,6 +66,8 @@ SIGNATURES = {
     "sbp_ctx_destroy": (c_i32, [c_void_p]),
     "sbp_ctx_device_info": (c_i32, [c_void_p, P(c_i32), P(c_i64), P(c_i64), P(c_i64)]),
     "sbp_ctx_launch_count": (c_i64, [c_void_p]),
+    "sbp_ctx_set_option": (c_i32, [c_void_p, C.c_char_p, c_i32]),
+    "sbp_ctx_get_option": (c_i32, [c_void_p, C.c_char_p, P(c_i32)]),
     "sbp_malloc": (c_i32, [c_void_p, c_size_t, P(c_void_p)]),
     "sbp_free": (c_i32, [c_void_p, c_void_p]),
     "sbp_ctx_pci_bus_id": (c_i32, [c_void_p, C.c_char_p, c_i32]),

@@ -13,6 +13,28 @@ namespace sbp {
 
 static thread_local std::string g_last_error;
 
+const TuneSpec kTuneSpec[T_COUNT] = {
+    {"sparse_logr", "SBP_SPARSE_LOGR", -1}, {"bsr_no_pairing", "SBP_BSR_NO_PAIRING", 0}, {"sparse_kernel", "SBP_SPARSE_KERNEL", 1},
+    {"sym_variant", "SBP_SYM_VARIANT", 1},  {"fused_stage", "SBP_FUSED_STAGE", 1},       {"solve_small", "SBP_SOLVE_SMALL", -1},
+    {"bsr_out", "SBP_BSR_OUT", 2},          {"bsr_mt", "SBP_BSR_MT", 0},                 {"bsr_depth", "SBP_BSR_DEPTH", 99},
+    {"bsr_mh", "SBP_BSR_MH", 0},            {"bsr_v3", "SBP_BSR_V3", -1},                {"bsr_cw", "SBP_BSR_CW", 8},
+    {"bsr_help", "SBP_BSR_HELP", 1},        {"bsr_skew", "SBP_BSR_SKEW", 0},             {"bsr_sem", "SBP_BSR_SEM", 0},
+    {"bsr_pf", "SBP_BSR_PF", -1},           {"bsr_verbose", "SBP_BSR_VERBOSE", 0},       {"gemm_variant", "SBP_GEMM_VARIANT", -2},
+    {"ds_v4", "SBP_DS_V4", 1},              {"sparse_db", "SBP_SPARSE_DB", 0}};
+
+static void tune_from_env(sbp_ctx* ctx) {
+    for (int k = 0; k < T_COUNT; k++) {
+        const char* e = getenv(kTuneSpec[k].env);
+        int v = kTuneSpec[k].def;
+        if (e) {
+            if (k == T_SPARSE_KERNEL && (strcmp(e, "sell") == 0 || strcmp(e, "bsr") == 0)) v = strcmp(e, "bsr") == 0;
+            else if (k == T_BSR_NO_PAIRING || k == T_BSR_VERBOSE) v = (*e && strcmp(e, "0") != 0) ? 1 : 0;
+            else v = atoi(e);
+        }
+        ctx->tune[k] = v;
+    }
+}
+
 void set_error(const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -232,9 +254,9 @@ static int32_t build_sell(sbp_op* op, int N, const std::vector<int>& rowptr, con
     int best_logR = 0;
     double best_cost = 1e300;
     std::vector<std::vector<int>> best_union;
-    const char* forced = getenv("SBP_SPARSE_LOGR");  // tuning/debug knob: force rows-per-lane = 1 << value
+    const int forced = op->ctx->tune[T_SPARSE_LOGR];  // tuning/debug knob: force rows-per-lane = 1 << value
     for (int logR = 0; logR <= 2; logR++) {
-        if (forced && atoi(forced) != logR) continue;
+        if (forced >= 0 && forced != logR) continue;
         const int R = 1 << logR;
         const int nrb = (N + R - 1) / R;
         std::vector<std::vector<int>> uni(nrb);
@@ -369,7 +391,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     std::vector<char> used(nq, 0);
     std::vector<int> rows;  // 2 per block: first row of quad A, first row of quad B (or >= N: none)
     const int none = 4 * nq + 4;
-    const bool pair_far = getenv("SBP_BSR_NO_PAIRING") == nullptr;
+    const bool pair_far = op->ctx->tune[T_BSR_NO_PAIRING] == 0;
     for (int qa = 0; qa < nq; qa++) {
         if (used[qa]) continue;
         used[qa] = 1;
@@ -718,6 +740,7 @@ int32_t sbp_ctx_create(int32_t device, sbp_ctx** out) {
     SBP_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     SBP_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    tune_from_env(ctx);
     for (int s = 0; s < 2; s++)
         for (int k = 0; k < 3; k++) SBP_CUDA(cudaEventCreateWithFlags(&ctx->pipe_ev[s][k], cudaEventDisableTiming));
     *out = ctx;
@@ -771,6 +794,26 @@ int32_t sbp_ctx_device_info(sbp_ctx* ctx, int32_t* sm_count, int64_t* l2_bytes, 
     return SBP_OK;
 }
 int64_t sbp_ctx_launch_count(sbp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+static int tune_index(const char* name) {
+    for (int k = 0; k < T_COUNT; k++)
+        if (strcmp(name, kTuneSpec[k].name) == 0 || strcmp(name, kTuneSpec[k].env) == 0) return k;
+    return -1;
+}
+int32_t sbp_ctx_set_option(sbp_ctx* ctx, const char* name, int32_t value) {
+    SBP_REQUIRE(ctx && name, SBP_EINVAL, "null argument");
+    const int k = tune_index(name);
+    SBP_REQUIRE(k >= 0, SBP_EINVAL, "unknown option '%s'", name);
+    ctx->tune[k] = value;
+    return SBP_OK;
+}
+int32_t sbp_ctx_get_option(sbp_ctx* ctx, const char* name, int32_t* value) {
+    SBP_REQUIRE(ctx && name && value, SBP_EINVAL, "null argument");
+    const int k = tune_index(name);
+    SBP_REQUIRE(k >= 0, SBP_EINVAL, "unknown option '%s'", name);
+    *value = ctx->tune[k];
+    return SBP_OK;
+}
 
 // ---- memory -------------------------------------------------------------------------------------
 int32_t sbp_malloc(sbp_ctx* ctx, size_t bytes, void** dptr) {
@@ -901,9 +944,8 @@ int32_t sbp_op_sparse_create(sbp_ctx* ctx, int32_t N, const int32_t* h_rowptr, c
     if (!rc) rc = upload(&op->d_csr_val, val);
     for (int r = 0; r < N; r++) op->csr_max_row = std::max(op->csr_max_row, rp[r + 1] - rp[r]);
     if (!rc) {
-        // kernel choice (SBP_SPARSE_KERNEL=sell|bsr overrides): the tensor-core kernel whenever a tile fits in smem
-        const char* e = getenv("SBP_SPARSE_KERNEL");
-        const bool want_bsr = e ? (strcmp(e, "bsr") == 0) : true;
+        // kernel choice (option sparse_kernel / SBP_SPARSE_KERNEL=sell|bsr overrides): the tensor-core kernel whenever a tile fits in smem
+        const bool want_bsr = ctx->tune[T_SPARSE_KERNEL] != 0;
         if (want_bsr && bsr_available(ctx, op)) op->variant = SBP_KERNEL_BSR_DMMA;
     }
     if (!rc && h_w) {
@@ -1071,14 +1113,7 @@ int32_t sbp_op_info(const sbp_op* op, int32_t* kind, int32_t* N, int32_t* G, int
 // ---- hot path -----------------------------------------------------------------------------------
 // tuning knob of the even/odd kernel (bit0 prefetch, bit1 one m-tile per warp, bit2 256-thread CTAs);
 // the default was picked from the sweep in profiles/ (tools/tune_sym.py)
-static int sym_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SBP_SYM_VARIANT");
-        v = e ? atoi(e) & 7 : 1;
-    }
-    return v;
-}
+static int sym_variant(const sbp_ctx* ctx) { return ctx->tune[T_SYM_VARIANT] & 7; }
 static int32_t check_batch(sbp_ctx* ctx, const sbp_op* op, const void* dU, const void* U, int64_t B) {
     SBP_REQUIRE(ctx && op, SBP_EINVAL, "null ctx/op");
     SBP_REQUIRE(op->ctx == ctx, SBP_EINVAL, "operator belongs to a different context");
@@ -1097,7 +1132,7 @@ int32_t sbp_apply(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, i
     SBP_CUDA(cudaSetDevice(ctx->device));
     switch (op->kind) {
         case SBP_OP_DENSE:
-            if (op->sym) return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, sym_variant());
+            if (op->sym) return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, nullptr, nullptr, sym_variant(ctx));
             if (is_small(op)) return launch_dense_small(ctx, op, dU, U, B, alpha, beta, false, nullptr, nullptr);
             return launch_dense_gemm(ctx, op, dU, U, B, alpha, beta);
         case SBP_OP_TABLE:
@@ -1130,7 +1165,7 @@ int32_t sbp_apply_table(sbp_ctx* ctx, const sbp_op* op, double* dU, const double
         return launch_integrate(ctx, op->d_w, op->N, 1, U, nullptr, B, 1, energy, energy_sum);
     }
     if (op_index == nullptr && op->sym)
-        return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, sym_variant());
+        return launch_dense_small_sym(ctx, op, dU, U, B, alpha, beta, energy, energy_sum, sym_variant(ctx));
     if (op_index == nullptr && is_small(op))
         return launch_dense_small(ctx, op, dU, U, B, alpha, beta, true, energy, energy_sum);
     return launch_table_generic(ctx, op, dU, U, B, op_index, alpha, beta, energy, energy_sum);
@@ -1203,7 +1238,7 @@ int32_t sbp_rhs_advection1d(sbp_ctx* ctx, const sbp_op* op, double* dU, const do
     else if (D->kind == SBP_OP_SPARSE)
         rc = launch_sparse_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, 0, op->d_a, &sat);
     else if (D->sym && op->d_a == nullptr)
-        rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant(), &sat);
+        rc = launch_dense_small_sym(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, sym_variant(ctx), &sat);
     else if (is_small(D))
         rc = launch_dense_small_ex(ctx, D, dU, U, B, -1.0, 0.0, nullptr, nullptr, op->d_a, &sat);
     else {
@@ -1232,10 +1267,7 @@ static int32_t ensure_stage_buf(sbp_ctx* ctx, size_t doubles) {
     ctx->stage_doubles = doubles;
     return SBP_OK;
 }
-static bool stage_fusion_enabled() {
-    const char* e = getenv("SBP_FUSED_STAGE");  // 0: always RHS + sbp_lincomb (A/B measurements)
-    return !e || atoi(e) != 0;
-}
+static bool stage_fusion_enabled(const sbp_ctx* ctx) { return ctx->tune[T_FUSED_STAGE] != 0; }  // 0: always RHS + sbp_lincomb
 
 int32_t sbp_rhs_advection2d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext, const double* U, int64_t B,
                                   const double* g, int64_t g_stride, double ca, double cb, const double* Uextra,
@@ -1249,7 +1281,7 @@ int32_t sbp_rhs_advection2d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext,
     SBP_CUDA(cudaSetDevice(ctx->device));
     const sbp_op* A = op->inner;
     const bool al = ((reinterpret_cast<uintptr_t>(Uextra) | reinterpret_cast<uintptr_t>(Unext)) & 15) == 0;
-    if (stage_fusion_enabled() && A->kind == SBP_OP_SPARSE && bsr_can_run(A, U) && al) {
+    if (stage_fusion_enabled(ctx) && A->kind == SBP_OP_SPARSE && bsr_can_run(A, U) && al) {
         const StageUpdate su{ca, cb, ch, Uextra};
         return launch_bsr(ctx, A, Unext, U, B, -1.0, 0.0, op, g, g_stride, nullptr, &su);
     }
@@ -1274,7 +1306,7 @@ int32_t sbp_rhs_advection1d_stage(sbp_ctx* ctx, const sbp_op* op, double* Unext,
     SBP_CUDA(cudaSetDevice(ctx->device));
     const sbp_op* D = op->inner;
     const bool al = ((reinterpret_cast<uintptr_t>(Uextra) | reinterpret_cast<uintptr_t>(Unext)) & 15) == 0;
-    if (stage_fusion_enabled() && D->kind == SBP_OP_SPARSE && bsr_can_run(D, U) && op->d_a == nullptr && al) {
+    if (stage_fusion_enabled(ctx) && D->kind == SBP_OP_SPARSE && bsr_can_run(D, U) && op->d_a == nullptr && al) {
         Sat1D sat;
         sat.bc = bc;
         sat.bc_stride = bc_stride;
@@ -1403,10 +1435,9 @@ int32_t sbp_solve_ssprk53(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B, 
     SBP_REQUIRE(bc_row_stride >= (two_d ? op->N : 2), SBP_EDIM, "bc_row_stride too small (%lld)", (long long)bc_row_stride);
     SBP_CUDA(cudaSetDevice(ctx->device));
     // small batches: the whole solve in ONE launch (a CTA per instance, state in shared memory; solve_small.cu) instead of
-    // 5 launches per step.  SBP_SOLVE_SMALL=0 forces the batched path, =1 the single launch whenever it is applicable.
+    // 5 launches per step.  Option solve_small (SBP_SOLVE_SMALL) = 0 forces the batched path, 1 the single launch whenever it is applicable.
     {
-        const char* e = getenv("SBP_SOLVE_SMALL");  // (once per solve, not per launch)
-        const int force = e ? atoi(e) : -1;
+        const int force = ctx->tune[T_SOLVE_SMALL];
         const bool applicable = solve_small_applies(ctx, op, force == 1 ? 1 : B);
         if (force != 0 && applicable) {
             void* d_h = nullptr;

@@ -563,7 +563,7 @@ static int32_t launch_bsr_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     if (per_sm < 1) per_sm = 1;
     const long long ntiles = (p.B + TI - 1) / TI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
-    if (getenv("SBP_BSR_VERBOSE")) fprintf(stderr, "k_bsr<%d,%d,%d,%d>: %d CTAs/SM, grid %d, %lld tiles\n", MTW, MH, SAT, OUT, per_sm, grid, ntiles);
+    if (ctx->tune[T_BSR_VERBOSE]) fprintf(stderr, "k_bsr<%d,%d,%d,%d>: %d CTAs/SM, grid %d, %lld tiles\n", MTW, MH, SAT, OUT, per_sm, grid, ntiles);
     kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
@@ -624,11 +624,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     }
     const int satmode = (adv && adv->d_rb_bdiag) ? 1 : (sat && sat->enabled ? 2 : 0);
     // output path: TMA tensor stores when dU is 16-byte aligned and beta == 0 (SBP_BSR_OUT=1 forces plain stores)
-    static int forced_out = -1;
-    if (forced_out < 0) {
-        const char* e = getenv("SBP_BSR_OUT");
-        forced_out = e ? atoi(e) : 2;
-    }
+    const int forced_out = ctx->tune[T_BSR_OUT];
     const bool aligned = (reinterpret_cast<uintptr_t>(dU) & 15) == 0;
     const bool odd = op->bsr_N != op->N;
     const int vec = !aligned ? 0 : (beta == 0.0 && forced_out == 2) ? 2 : 1;
@@ -668,13 +664,7 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     // (instances per tile, pipeline depth): the largest tile that still allows one chunk of lookahead (operator
     // fragments are re-read from L2 once per tile), then the deepest pipeline that fits; small batches use smaller
     // tiles so that every SM gets work.  SBP_BSR_MT / SBP_BSR_DEPTH override (tuning).
-    static int forced_mt = -1, forced_d = -1;
-    if (forced_mt < 0) {
-        const char* e = getenv("SBP_BSR_MT");
-        forced_mt = e ? atoi(e) : 0;
-        e = getenv("SBP_BSR_DEPTH");
-        forced_d = e ? atoi(e) : 99;
-    }
+    const int forced_mt = ctx->tune[T_BSR_MT], forced_d = ctx->tune[T_BSR_DEPTH];
     int MT = 8;
     auto smaller = [](int mt) { return mt > 4 ? mt - 1 : mt >> 1; };
     while (MT > 1 && !bsr_fits(ctx, op, MT, 1)) MT = smaller(MT);
@@ -691,16 +681,12 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.nst = D + 1;
     p.item = reinterpret_cast<const int4*>(op->d_bsr_item) + (size_t)D * p.nch * kBsrCH * 2;
     const size_t smem = bsr_smem(op, MT, D);
-    static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
+    const bool verbose = ctx->tune[T_BSR_VERBOSE] != 0;
     if (verbose)
         fprintf(stderr, "k_bsr: N=%d B=%lld nrb=%d nch=%d frags=%lld maxf=%d MT=%d stages=%d nbox=%d smem=%zu sat=%d out=%d\n", p.N,
                 (long long)B, p.nrb, p.nch, (long long)op->bsr_frags, p.maxf, MT, D + 1, p.nbox, smem, satmode, vec);
     // one consumer warp per row block of the chunk, MT m-tiles each (SBP_BSR_MH=2: two warps per row block, MT/2 each)
-    static int forced_mh = -1;
-    if (forced_mh < 0) {
-        const char* e = getenv("SBP_BSR_MH");
-        forced_mh = e ? atoi(e) : 0;
-    }
+    const int forced_mh = ctx->tune[T_BSR_MH];
     if (forced_mh == 2 && MT >= 2) {
         switch (MT) {
             case 8: return launch_bsr_mt<4, 2>(ctx, p, smem, satmode, vec);

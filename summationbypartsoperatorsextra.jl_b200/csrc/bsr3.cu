@@ -730,30 +730,19 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
 
 // p arrives filled in by launch_bsr (operator, batch view, SAT data); returns false when this kernel does not apply
 bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int out, int32_t* rc) {
-    // SBP_BSR_V3 (read at every launch: the tests switch it): 0 / unset = k_bsr, 1 = this kernel for large batches, 2 = always
-    static int forced_mt = -1, forced_d = 99;
-    if (forced_mt < 0) {
-        const char* e = getenv("SBP_BSR_MT");
-        forced_mt = e ? atoi(e) : 0;
-        e = getenv("SBP_BSR_DEPTH");
-        forced_d = e ? atoi(e) : 99;
-    }
+    // option bsr_v3 (SBP_BSR_V3): 0 = k_bsr, 1 = this kernel for large batches, 2 = always
+    const int forced_mt = ctx->tune[T_BSR_MT], forced_d = ctx->tune[T_BSR_DEPTH];
     // Default rule (measured, profiles/r1k_bsr3_notes.txt section 5): with the store-helper warps this kernel beats k_bsr on
     // every RHS launch (2D or 1D SATs fused) and on instance-pair views (odd N), by 2-18 %; k_bsr stays ahead on plain
-    // even-N applies.  SBP_BSR_V3 (read at every launch: the tests switch it): unset = that rule, 0 = always k_bsr,
+    // even-N applies.  option bsr_v3 (SBP_BSR_V3): -1 = that rule, 0 = always k_bsr,
     // 1 = this kernel for every large batch, 2 = always this kernel.
-    const char* ev = getenv("SBP_BSR_V3");
-    const int enabled = ev ? atoi(ev) : -1;
+    const int enabled = ctx->tune[T_BSR_V3];
     if (!enabled || kBsrGroups != 1 || op->d_bsr_pos3 == nullptr) return false;
     // (r2: also plain applies of operators whose tile row is much longer than the ring -- 2D clouds: config 3's A without the
     // SAT terms 0.322 ms on k_bsr, 0.280 here)
     const bool wide = p.nbt > 2 * op->bsr_nbox[1];
     if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N || wide))) return false;
-    // (read at every launch: the tests switch them)
-    const char* ecw = getenv("SBP_BSR_CW");
-    const int forced_cw = ecw ? atoi(ecw) : 8;
-    const char* eh = getenv("SBP_BSR_HELP");
-    const int help = eh ? atoi(eh) : 1;
+    const int forced_cw = ctx->tune[T_BSR_CW], help = ctx->tune[T_BSR_HELP];
     // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
     const int cw = (forced_cw == 12 && out != 0 && !p.fused) ? 12 : (help && out == 2) ? 9 : 8;
     // fused stage updates: helper variant of an RHS launch (the extra operand travels through the staging buffers: the
@@ -777,21 +766,13 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     p.item = reinterpret_cast<const int4*>(op->d_bsr_item) + (size_t)D * p.nch * kBsrCH * 2;
     p.pos = op->d_bsr_pos3 + (size_t)(MT - 1) * (size_t)std::max<int64_t>(op->bsr_frags, 1) * 4;
     const size_t smem = bsr3_smem(op, MT, D, out, cw);
-    {
-        static int skew = -1;
-        if (skew < 0) {
-            const char* e = getenv("SBP_BSR_SKEW");
-            skew = e ? atoi(e) : 0;
-        }
-        p.skew = skew;
-        const char* es = getenv("SBP_BSR_SEM");
-        p.sem = es ? atoi(es) : 0;
-        const char* ep = getenv("SBP_BSR_PF");
-        // default: 5 boxes ahead when a tile row is much longer than the ring (2D clouds: config 3 0.312 -> 0.291 ms, N = 900 / 1936
-        // -5 / -4 %); banded 1D operators, whose ring holds most of the row, lose 6-13 % with any prefetch (profiles/r2_bsr_notes.txt)
-        p.pf = std::min(ep ? atoi(ep) : (p.nbt > 2 * p.nbox ? 5 : 0), p.nbt - 1);
-    }
-    static const bool verbose = getenv("SBP_BSR_VERBOSE") != nullptr;
+    p.skew = ctx->tune[T_BSR_SKEW];
+    p.sem = ctx->tune[T_BSR_SEM];
+    // L2 prefetch distance of the box producer: 5 boxes ahead when a tile row is much longer than the ring (2D clouds: config 3
+    // 0.312 -> 0.291 ms, N = 900 / 1936 -5 / -4 %); banded 1D operators, whose ring holds most of the row, lose 6-13 % with any
+    // prefetch (profiles/r2_bsr_notes.txt)
+    p.pf = std::min(ctx->tune[T_BSR_PF] >= 0 ? ctx->tune[T_BSR_PF] : (p.nbt > 2 * p.nbox ? 5 : 0), p.nbt - 1);
+    const bool verbose = ctx->tune[T_BSR_VERBOSE] != 0;
     if (verbose)
         fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d cw=%d\n",
                 p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out, cw);

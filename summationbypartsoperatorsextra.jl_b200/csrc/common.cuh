@@ -48,6 +48,38 @@ constexpr int kBsrDepths = 8;          // pipeline depths (chunks of lookahead) 
 static_assert(kBsrBX % 16 == 4, "box rows must be 4 (mod 16) doubles");
 constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
 
+// Tuning / debugging knobs.  Each is read from its environment variable ONCE, when a context is created, and can be changed
+// per context with sbp_ctx_set_option (the tests and the sweep tools do); nothing on a launch path calls getenv.
+enum Tune {
+    T_SPARSE_LOGR,     // SBP_SPARSE_LOGR     -1    sparse.cu: force rows per lane = 1 << value
+    T_BSR_NO_PAIRING,  // SBP_BSR_NO_PAIRING   0    build_bsr: pair each quad with its successor only
+    T_SPARSE_KERNEL,   // SBP_SPARSE_KERNEL    1    kernel of a sparse operator chosen at upload: 1 / "bsr" block-sparse DMMA, 0 / "sell"
+    T_SYM_VARIANT,     // SBP_SYM_VARIANT      1    even/odd kernel: bit0 prefetch, bit1 one m-tile per warp, bit2 256-thread CTAs
+    T_FUSED_STAGE,     // SBP_FUSED_STAGE      1    0: stage updates as RHS + sbp_lincomb
+    T_SOLVE_SMALL,     // SBP_SOLVE_SMALL     -1    single-launch solve: -1 by batch size, 0 never, 1 whenever applicable
+    T_BSR_OUT,         // SBP_BSR_OUT          2    2 TMA tensor stores, 1 plain 16-byte stores
+    T_BSR_MT,          // SBP_BSR_MT           0    force the m-tiles per warp (tile = 8 MT instances)
+    T_BSR_DEPTH,       // SBP_BSR_DEPTH       99    cap of the box pipeline depth
+    T_BSR_MH,          // SBP_BSR_MH           0    2: two warps per row block (k_bsr)
+    T_BSR_V3,          // SBP_BSR_V3          -1    -1 default rule, 0 always k_bsr, 1 k_bsr3 for large batches, 2 always k_bsr3
+    T_BSR_CW,          // SBP_BSR_CW           8    consumer warps of k_bsr3 (8 or 12)
+    T_BSR_HELP,        // SBP_BSR_HELP         1    store-helper warps
+    T_BSR_SKEW,        // SBP_BSR_SKEW         0    start-up delay (cycles) of every second consumer warp
+    T_BSR_SEM,         // SBP_BSR_SEM          0    12 consumer warps: at most this many of a scheduler's three multiply at a time
+    T_BSR_PF,          // SBP_BSR_PF          -1    L2 prefetch distance of the box producer in boxes (-1: by the shape of the tile)
+    T_BSR_VERBOSE,     // SBP_BSR_VERBOSE      0    print the launch geometry
+    T_GEMM_VARIANT,    // SBP_GEMM_VARIANT    -2    < 0: TMA pipeline, >= 0: one of the cp.async configurations
+    T_DS_V4,           // SBP_DS_V4            1    256-bit small-dense kernel variant (-1: off)
+    T_SPARSE_DB,       // SBP_SPARSE_DB        0    double buffering of the SELL kernel
+    T_COUNT
+};
+struct TuneSpec {
+    const char* name;  // option name for sbp_ctx_set_option ("bsr_v3", ...)
+    const char* env;
+    int def;
+};
+extern const TuneSpec kTuneSpec[T_COUNT];
+
 }  // namespace sbp
 
 struct sbp_ctx {
@@ -69,6 +101,7 @@ struct sbp_ctx {
     size_t pipe_bytes = 0;
     cudaEvent_t pipe_ev[2][3] = {};
     void* nccl_comm = nullptr;
+    int tune[sbp::T_COUNT] = {};  // tuning knobs (sbp::Tune), environment defaults taken at creation
     // grow-only device buffers of the *_host / solve entry points: [0] boundary data, [1] Runge-Kutta work vectors, [2] state
     // [3] step sizes of the single-launch solve
     void* aux[4] = {nullptr, nullptr, nullptr, nullptr};

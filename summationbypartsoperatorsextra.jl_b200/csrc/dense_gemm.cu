@@ -318,11 +318,7 @@ static int32_t launch_gemm_tma(sbp_ctx* ctx, const sbp_op* op, double* dU, const
 int32_t launch_dense_gemm(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, int64_t B, double alpha,
                           double beta) {
     // tuning knob SBP_GEMM_VARIANT (tools/time_config.py --workload config5 sweeps it)
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("SBP_GEMM_VARIANT");
-        v = e ? atoi(e) : -2;
-    }
+    const int v = ctx->tune[T_GEMM_VARIANT];
     // default: the TMA pipeline (needs 16-byte aligned rows: N even, aligned base pointers, B < 2^31); SBP_GEMM_VARIANT
     // >= 0 selects one of the cp.async configurations, which also serve the unaligned cases
     const bool tma_ok = (op->N % 2 == 0) && ((reinterpret_cast<uintptr_t>(U) & 15) == 0) &&

@@ -327,11 +327,7 @@ int32_t launch_dense_small_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const 
     const bool skip = band > 0 && !want_energy;
     // 256-bit variant (N % 16 == 0, 32-byte aligned batches, no column scaling, no zero-fragment skipping);
     // SBP_DS_V4 = -1 disables it, otherwise its low bits select the variant (dense_small_v4.cu)
-    static int v4 = -2;
-    if (v4 == -2) {
-        const char* e = getenv("SBP_DS_V4");
-        v4 = e ? atoi(e) : 1;
-    }
+    const int v4 = ctx->tune[T_DS_V4];
     if (v4 >= 0 && !skip && sat == nullptr && op->d_frag4 && cfrag == nullptr &&
         ((reinterpret_cast<uintptr_t>(U) & 31) == 0) &&
         ((reinterpret_cast<uintptr_t>(dU) & 31) == 0))

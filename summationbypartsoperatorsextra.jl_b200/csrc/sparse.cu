@@ -362,11 +362,7 @@ int32_t launch_sparse_ex(sbp_ctx* ctx, const sbp_op* op, double* dU, const doubl
         // double buffering (tuning knob SBP_SPARSE_DB=0/1).  Measured on config 3 (profiles/r1c_sparse_sweep.txt): two
         // single-buffered CTAs per SM overlap staging and compute as well as one double-buffered CTA does, and keep
         // more warps resident, so it is off by default.
-        static int db_env = -1;
-        if (db_env < 0) {
-            const char* e = getenv("SBP_SPARSE_DB");
-            db_env = e ? (atoi(e) ? 1 : 0) : 0;
-        }
+        const int db_env = ctx->tune[T_SPARSE_DB];
         const bool db = db_env && 2 * (size_t)p.n_slots * kT * sizeof(double) <= budget;
         if (db) {
             switch (op->logR) {

@@ -60,6 +60,32 @@ class Context:
         check(self._lib.sbp_ctx_get_stream(self.handle, C.byref(s)))
         return s.value or 0
 
+    def set_option(self, name: str, value: int):
+        """Tuning / debugging option of this context (`sbp_ctx_set_option`; names: csrc/common.cuh enum Tune)."""
+        check(self._lib.sbp_ctx_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int32()
+        check(self._lib.sbp_ctx_get_option(self.handle, name.encode(), C.byref(v)))
+        return v.value
+
+    def options(self, **kv):
+        """Context manager: set options for the duration of a `with` block, then restore the previous values."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            old = {k: self.get_option(k) for k in kv}
+            try:
+                for k, v in kv.items():
+                    self.set_option(k, v)
+                yield self
+            finally:
+                for k, v in old.items():
+                    self.set_option(k, v)
+
+        return scope()
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.sbp_ctx_launch_count(self.handle))

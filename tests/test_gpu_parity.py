@@ -24,6 +24,19 @@ def ctx():
     c.close()
 
 
+OPTION_NAMES = ("sparse_kernel", "bsr_v3", "bsr_cw", "bsr_help", "fused_stage", "solve_small", "bsr_mt", "bsr_depth", "bsr_pf",
+                "bsr_out", "bsr_sem")
+
+
+@pytest.fixture(autouse=True)
+def _restore_options(ctx):
+    """tests switch kernel families through context options (sbp_ctx_set_option); every test starts from the defaults"""
+    saved = {k: ctx.get_option(k) for k in OPTION_NAMES}
+    yield
+    for k, v in saved.items():
+        ctx.set_option(k, v)
+
+
 def rel_err(Y, Yref):
     """per-instance norm-wise relative error, max over the batch"""
     Y, Yref = np.atleast_2d(Y), np.atleast_2d(Yref)
@@ -263,24 +276,24 @@ def test_apply_large_dense(ctx, N, B):
 
 # ---- K2: structurally sparse operators ---------------------------------------------------------------------------
 @pytest.fixture(params=["bsr3", "bsr", "sell"])
-def sparse_kernel(request, monkeypatch):
+def sparse_kernel(request, ctx):
     """all sparse kernels: block-sparse DMMA with the lean consumer loop (bsr3.cu, default for large batches; forced
     here for every batch size), its first generation (bsr.cu, small batches) and the scalar row-blocked SELL kernel
-    (sparse.cu); SBP_SPARSE_KERNEL is read by sbp_op_sparse_create at every upload, SBP_BSR_V3 at every launch"""
-    monkeypatch.setenv("SBP_SPARSE_KERNEL", "sell" if request.param == "sell" else "bsr")
-    monkeypatch.setenv("SBP_BSR_V3", "2" if request.param == "bsr3" else "0")
-    return {"bsr3": "bsr_dmma", "bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
+    (sparse.cu); option sparse_kernel is read by sbp_op_sparse_create at every upload, bsr_v3 at every launch"""
+    with ctx.options(sparse_kernel=0 if request.param == "sell" else 1, bsr_v3=2 if request.param == "bsr3" else 0):
+        yield {"bsr3": "bsr_dmma", "bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
 
 
-@pytest.fixture(params=["helpers", "plain", "cw12", "k_bsr"])
-def bsr_generation(request, monkeypatch):
+BSR_ORGANISATIONS = {"helpers": {"bsr_v3": 2}, "plain": {"bsr_v3": 2, "bsr_help": 0},
+                     "cw12": {"bsr_v3": 2, "bsr_help": 0, "bsr_cw": 12}, "k_bsr": {"bsr_v3": 0}}
+
+
+@pytest.fixture(params=list(BSR_ORGANISATIONS))
+def bsr_generation(request, ctx):
     """block-sparse kernel generation / warp organisation: bsr3.cu forced with store-helper warps (the default for RHS
     launches), without them, with 12 consumer warps, and bsr.cu"""
-    env = {"helpers": {"SBP_BSR_V3": "2"}, "plain": {"SBP_BSR_V3": "2", "SBP_BSR_HELP": "0"},
-           "cw12": {"SBP_BSR_V3": "2", "SBP_BSR_HELP": "0", "SBP_BSR_CW": "12"}, "k_bsr": {"SBP_BSR_V3": "0"}}[request.param]
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    return request.param
+    with ctx.options(**BSR_ORGANISATIONS[request.param]):
+        yield request.param
 
 
 @pytest.mark.parametrize("order,N", [(2, 101), (4, 101), (4, 102), (4, 400), (2, 1500)])
@@ -675,7 +688,7 @@ def test_solve_ssprk53_host_and_pcie_probe(ctx):
 
 @pytest.mark.parametrize("case", ["1d_sparse", "1d_dense", "1d_variable_speed", "2d_sparse", "2d_dense"])
 @pytest.mark.parametrize("B", [1, 5, 64])
-def test_solve_ssprk53_single_launch(ctx, case, B, monkeypatch):
+def test_solve_ssprk53_single_launch(ctx, case, B):
     """Small batches: the whole fixed-step SSPRK53 solve runs in ONE launch (k_solve_ssprk53_small: a CTA per instance, state
     in shared memory) instead of five launches per step.  Checked against the oracle's SSPRK53 on the same operator and against
     the batched path (SBP_SOLVE_SMALL=0) -- config 1 of BASELINE (examples/RBF_FSBP_advection.jl) at B = 1 is this path."""
@@ -707,12 +720,13 @@ def test_solve_ssprk53_single_launch(ctx, case, B, monkeypatch):
     tab = ctx.upload_array(np.ascontiguousarray(table))
     res = {}
     for force in ("1", "0"):
-        monkeypatch.setenv("SBP_SOLVE_SMALL", force)
+        ctx.set_option("solve_small", int(force))
         u = ctx.upload(U0)
         n0 = ctx.launch_count
         S._lib.check(ctx._lib.sbp_solve_ssprk53(ctx.handle, op.handle, C.c_void_p(u.ptr), B, C.c_void_p(tab.ptr),
                                                 table.shape[1], nsteps, hs.ctypes.data_as(C.c_void_p), None))
         res[force] = (u.to_host(), ctx.launch_count - n0)
+    ctx.set_option("solve_small", -1)
     assert res["1"][1] == 1 and res["0"][1] >= 5 * nsteps  # one launch against five (or more) per step
     ref = U0.copy()
     for b in range(B):
@@ -774,6 +788,34 @@ def test_error_norm_reduction(ctx):
                                          C.byref(out)))
     r = ut / (1e-6 + np.maximum(np.abs(up), np.abs(u)) * 1e-3)
     assert abs(out.value - np.sqrt(np.mean(r * r))) <= 1e-13 * out.value
+
+
+@pytest.mark.parametrize("organisation", list(BSR_ORGANISATIONS))
+def test_block_sparse_kernels_are_deterministic(ctx, organisation):
+    """Race detector (compute-sanitizer is not available on this pool): 100 launches of the fused 2D RHS in each warp
+    organisation of the block-sparse kernels (store-helper warps, plain, 12 consumer warps, k_bsr) must be BITWISE equal --
+    the mbarrier / TMA pipelines have no data-dependent ordering, so any difference is a visibility race."""
+    D = _scattered_mfsbp(20, seed=9)  # N = 400: several chunks, a ring that wraps
+    a = (1.0, 0.7)
+    g = lambda x, t: np.sin(2 * x[0] + x[1] - t)
+    semi = S.MultidimensionalLinearAdvectionNonperiodicSemidiscretization(D, a, g, storage="sparse")
+    B = 148 * 56 * 2 + 19  # two tiles per SM at the largest tile size + a ragged tail
+    u, du = ctx.upload(rand_batch(B, D.N, 41)), S.DeviceBatch.empty(ctx, B, D.N)
+    e, out = ctx.upload(rand_batch(B, D.N, 42)), S.DeviceBatch.empty(ctx, B, D.N)
+    with ctx.options(**BSR_ORGANISATIONS[organisation]):
+        semi(du, u, None, 0.3)
+        first = du.to_host()
+        semi.stage(out, u, 0.3, 0.6, 1e-3, 0.4, e)
+        first_stage = out.to_host()
+        for rep in range(100):
+            semi(du, u, None, 0.3)
+            semi.stage(out, u, 0.3, 0.6, 1e-3, 0.4, e)
+            if rep % 10 == 9:
+                assert np.array_equal(du.to_host(), first) and np.array_equal(out.to_host(), first_stage), rep
+    semio = O.AdvectionSemi2D(_oracle_md(D), a, g, D.corners)
+    U = u.to_host()
+    for b in (0, B // 2, B - 1):
+        assert rel_err(first[b], semio.rhs(U[b], 0.3)) <= TOL
 
 
 # ---- full-size configurations through size-independent properties ---------------------------------------------------
@@ -910,8 +952,8 @@ def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B, bsr_generation):
 @pytest.mark.parametrize("n1,storage", [(12, "sparse"), (9, "sparse"), (12, "dense")])  # N = 144 even, 81 odd (pairs), dense fallback
 @pytest.mark.parametrize("B", [1, 2, 65, 1027])
 @pytest.mark.parametrize("fused", ["1", "0"])
-def test_stage_update_advection2d(ctx, n1, storage, B, fused, monkeypatch):
-    monkeypatch.setenv("SBP_FUSED_STAGE", fused)
+def test_stage_update_advection2d(ctx, n1, storage, B, fused):
+    ctx.set_option("fused_stage", int(fused))
     D = _scattered_mfsbp(n1, seed=5)
     a = (0.6, -1.0)
     g = lambda x, t: np.cos(2 * x[0] - x[1] + t)
@@ -939,8 +981,8 @@ def test_stage_update_advection2d(ctx, n1, storage, B, fused, monkeypatch):
 @pytest.mark.parametrize("N,storage", [(101, "sparse"), (104, "sparse"), (64, "dense")])
 @pytest.mark.parametrize("B", [1, 3, 130, 1030])
 @pytest.mark.parametrize("fused", ["1", "0"])
-def test_stage_update_advection1d(ctx, N, storage, B, fused, monkeypatch):
-    monkeypatch.setenv("SBP_FUSED_STAGE", fused)
+def test_stage_update_advection1d(ctx, N, storage, B, fused):
+    ctx.set_option("fused_stage", int(fused))
     D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
     D.storage = storage
     Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
