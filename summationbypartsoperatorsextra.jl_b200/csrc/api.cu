@@ -574,6 +574,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
         pos.assign(PS, 0);
     }
     int32_t rc = upload(&op->d_bsr_val, frag);
+
     if (!rc) rc = upload(&op->d_bsr_pos, pos);
     if (pos3.empty()) pos3.assign(8 * PS, 0);
     if (!rc) rc = upload(&op->d_bsr_pos3, pos3);

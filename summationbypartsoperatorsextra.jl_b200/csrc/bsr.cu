@@ -531,7 +531,24 @@ static PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // 2-D tensor map over a row-major [B][N] array of doubles with boxes of box_nodes x box_inst (also used by dense_gemm.cu)
+// A tensor map is a pure function of (base address, N, B, box): time steppers launch on the same few batches thousands of
+// times, so the last encodings are kept (per host thread, 16 entries, round robin) instead of re-encoding 2-3 maps per launch.
 int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int box_nodes, int box_inst) {
+    struct Entry {
+        const double* base;
+        long long B;
+        int N, bn, bi;
+        CUtensorMap map;
+    };
+    static thread_local Entry cache[16];
+    static thread_local int used = 0, next = 0;
+    for (int k = 0; k < used; k++) {
+        const Entry& e = cache[k];
+        if (e.base == base && e.B == B && e.N == N && e.bn == box_nodes && e.bi == box_inst) {
+            *tm = e.map;
+            return SBP_OK;
+        }
+    }
     PFN_tmapEncodeTiled enc = tmap_encoder();
     SBP_REQUIRE(enc != nullptr, SBP_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)B};
@@ -542,6 +559,10 @@ int32_t make_tmap(CUtensorMap* tm, const double* base, int N, long long B, int b
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SBP_REQUIRE(r == CUDA_SUCCESS, SBP_ECUDA, "cuTensorMapEncodeTiled failed (%d) for N=%d B=%lld", (int)r, N, B);
+    Entry& e = cache[next];
+    e.base = base, e.B = B, e.N = N, e.bn = box_nodes, e.bi = box_inst, e.map = *tm;
+    next = (next + 1) % 16;
+    used = std::min(used + 1, 16);
     return SBP_OK;
 }
 

@@ -46,7 +46,23 @@
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
 
+#ifndef SBP_B3_TRACE
+#define SBP_B3_TRACE 0  // 1: clock64 stamps of CTA 0 into a global buffer (sbp_debug_set_trace), tools/trace_bsr3.py draws the timeline
+#endif
+
 namespace sbp {
+
+#if SBP_B3_TRACE
+__device__ long long* g_b3_trace = nullptr;  // [32 warps][kTraceItems][8 stamps]
+constexpr int kTraceItems = 96;
+#define B3_TR(w, it, idx)                                                                               \
+    do {                                                                                                \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && g_b3_trace && (it) < kTraceItems)            \
+            g_b3_trace[((w) * kTraceItems + (it)) * 8 + (idx)] = clock64();                             \
+    } while (0)
+#else
+#define B3_TR(w, it, idx) do { } while (0)
+#endif
 
 #if SBP_B3_EXP == 1
 #define B3_DMMA(c0, c1, a, b) asm volatile("" ::"d"(a), "d"(b))
@@ -166,6 +182,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         if (lane == 0) {
             const int h = warp - (CONS + 2);
             int c = 0, ph = 0;
+#if SBP_B3_TRACE
+            int trh = 0;
+#endif
             const int4* rec = p.item;
             int rowA[2], rowB[2];
             for (int k = 0; k < 2; k++) {
@@ -197,6 +216,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     for (int k = 0; k < 2; k++) {
                         const int w = h + 4 * k;
                         mbar_wait(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
+                        B3_TR(warp, trh, 2 * k);
                         if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
                         const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
                         if (rowA[k] < N) {
@@ -207,7 +227,11 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         }
                         if (XT && nb0 >= 0) load_extra(w, nA[k], nB[k], nb0);  // the buffer is free: fetch the next block's operand
                         mbar_arrive(&out_empty[w]);
+                        B3_TR(warp, trh, 2 * k + 1);
                     }
+#if SBP_B3_TRACE
+                    trh++;
+#endif
                     for (int k = 0; k < 2; k++) rowA[k] = nA[k], rowB[k] = nB[k];
                     c = cn;
                     ph ^= 1;
@@ -225,6 +249,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             uint64_t* const pfull = boxes ? bar_full : fbar_full;
             uint64_t* const pempty = boxes ? bar_empty : fbar_empty;
             int st = 0, round = 0, slot = 0;
+#if SBP_B3_TRACE
+            int trp = 0;
+#endif
             const uint32_t s_u32 = smem_u32(s_u), s_val32 = smem_u32(s_val), s_pos32 = smem_u32(s_pos);
             const uint32_t full32 = smem_u32(pfull);
             int4 cm = __ldg(p.chmeta);
@@ -234,6 +261,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 for (int c = 0; c < p.nch; c++) {
                     const int4 cmn = __ldg(p.chmeta + (c + 1 < p.nch ? c + 1 : 0));
                     if (round > 0) mbar_wait(&pempty[st], (round - 1) & 1);
+                    B3_TR(warp, trp, 0);
                     const uint32_t bar = full32 + 8u * st;
                     if (boxes) {
                         const int jn = cm.w;
@@ -277,6 +305,10 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                                 : "memory");
                         }
                     }
+                    B3_TR(warp, trp, 1);
+#if SBP_B3_TRACE
+                    trp++;
+#endif
                     if (++st == pst) st = 0, round++;
                     cm = cmn;
                 }
@@ -362,6 +394,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
     constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0 && !HELP;
     int out_phase = 0, ext_phase = 0;
+#if SBP_B3_TRACE
+    int trit = 0;
+#endif
     int sem_n = warp >> 2;  // CW == 12: index of this warp's next block among the blocks of its scheduler (rotation of three warps)
     double accs[DEFER ? 2 : 1][MT][2];
     int pv_rowA = 0, pv_rowB = 0, pv_b0 = 0, pv_state = 0;  // deferred block: rows of its quads, first tensor row, 1 = pending | 2 = scale | 4 = set
@@ -389,6 +424,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
      for (int hf = 0; hf < (DEFER ? 2 : 1); hf++) {
       if (tile >= ntlr) goto done;
       if (CW == kBsrCH || skip == 0) {
+        B3_TR(warp, trit, 0);
         const Rec r1 = load_rec(kBsrCH * pc + ps);
         advance();
         const int nf = r0.a.y;
@@ -438,6 +474,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // the operator fragments arrive ahead of the boxes: the first B operand and the ring addresses of the first two
         // fragments are fetched before the wait for the boxes
         mbar_wait(&fbar_full[fst], fphase);
+        B3_TR(warp, trit, 1);
         double b0v = 0.0;
         uint32_t adr0 = su32, adr = su32;
         if (work) {
@@ -446,6 +483,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
         }
         mbar_wait(&bar_full[st], phase);
+        B3_TR(warp, trit, 2);
         if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
         if (CW == 12 && p.sem) {  // block sem_n of this scheduler may multiply once sem_n - p.sem + 1... of its predecessors have finished
             const uint32_t a = smem_u32(&sem_fin[warp & 3]);
@@ -458,6 +496,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         if (work) {
             double a0[MT], a1[MT];
             lds_tiles<MT, MTB>(a0, adr0);
+            B3_TR(warp, trit, 3);
             int rem = nf;
             while (rem >= 2) {
 #if SBP_B3_EXP != 2
@@ -487,6 +526,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
 
+        B3_TR(warp, trit, 4);
         const int nb = min(Bir - b0, TI);
         if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the other warp of this scheduler may start
         if (CW == 12 && p.sem) {
@@ -594,6 +634,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             mbar_arrive(&bar_empty[st]);    // the ring slots behind this item's window may be refilled
             mbar_arrive(&fbar_empty[fst]);  // and so may the fragment buffers
         }
+        B3_TR(warp, trit, 5);
 
         if (SBP_B3_EXP == 4) {
             if (acc[0][0] == 1.2345e300) p.dU[0] = acc[MT - 1][1];
@@ -604,6 +645,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         } else if (HELP) {
             // ---- results to the warp's staging buffer; a helper warp stores them (every item signals, active or not) ----
             mbar_wait(&out_empty[warp], out_phase ^ 1);  // the helper has stored the previous contents (first item: passes)
+            B3_TR(warp, trit, 6);
             out_phase ^= 1;
             if (active) {
 #pragma unroll
@@ -612,6 +654,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
             __syncwarp();  // orders the lanes' stores before lane 0's arrive (release)
             if (lane == 0) mbar_arrive(&out_full[warp]);
+            B3_TR(warp, trit, 7);
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
             //      one lane stores quad A and quad B as {4 rows x 8*MT instances} boxes ----
@@ -641,6 +684,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
         r0 = r1;
+#if SBP_B3_TRACE
+        trit++;
+#endif
         skip = (myslot + CW) / kBsrCH - 1;
         myslot = (myslot + CW) & (kBsrCH - 1);
       } else {
@@ -787,3 +833,9 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
 }
 
 }  // namespace sbp
+
+#if SBP_B3_TRACE
+extern "C" int32_t sbp_debug_set_trace(void* dptr) {
+    return cudaMemcpyToSymbol(sbp::g_b3_trace, &dptr, sizeof(void*)) == cudaSuccess ? 0 : -3;
+}
+#endif
