@@ -282,6 +282,25 @@ int32_t sbp_solve_3sp_fsal(sbp_ctx* ctx, const sbp_op* op, double* U, int64_t B,
 int32_t sbp_error_norm(sbp_ctx* ctx, const double* utilde, const double* uprev, const double* u, int64_t n, double abstol,
                        double reltol, double* h_rms);
 
+/* ---- operator construction: batched objective evaluation ----------------------------------- */
+/* f(x) of the function-space-operator construction for C candidate parameter vectors at once (one CTA per candidate).
+ * Reference, one x per call: optimization_function_function_space_operator (ext/function_space_operators_optim.jl:89-105):
+ *   f(x) = sum |S(sigma) V - P(rho) V_x + R|^2, x = [sigma (L); rho (N)], P = diag(sig.(rho)) vol / sum(sig.(rho)), sig = logistic;
+ * and optimization_function_multidimensional_function_space_operator (ext/multidimensional_function_space_operators.jl:124-161):
+ *   f(x) = sum_d ( |S_d V - P V_xd + B_d(phi) V / 2|^2 + |V' B_d(phi) V - M_d|^2 ), x = [sigma_1; ..; sigma_D; rho (N); phi (Nb)].
+ * S_d is given by its index map (what set_S! of ext/utils.jl:83-148 writes) as CSR rows per direction: row i of S_d has the entries
+ * sign[j] * x[xidx[j]] in column col[j], j in [rowptr[d*(N+1)+i], rowptr[d*(N+1)+i+1]).  V: N x K, V_x: D x N x K, R: D x N x K
+ * (constant part of the residual, NULL = 0), M: D x K x K moments (NULL: no moment term), all row-major; boundary map (NULL for
+ * the 1D objective): bidx[d*N+k] = index j into phi of the boundary entry that set_B! leaves at node k (-1: none),
+ * bn[d*N+k] = normals[j][d].  X: device, C rows of Ltot + N + Nb doubles; out: device, C doubles. */
+typedef struct sbp_objective sbp_objective;
+int32_t sbp_objective_create(sbp_ctx* ctx, int32_t N, int32_t K, int32_t D, int32_t Nb, int64_t Ltot, const int32_t* h_rowptr,
+                             const int32_t* h_col, const int32_t* h_xidx, const double* h_sign, const double* h_V,
+                             const double* h_Vx, const double* h_R, const double* h_M, const int32_t* h_bidx,
+                             const double* h_bn, double vol, sbp_objective** out);
+int32_t sbp_objective_eval(sbp_ctx* ctx, const sbp_objective* obj, const double* X, int64_t C, double* out);
+int32_t sbp_objective_destroy(sbp_objective* obj);
+
 /* ---- host-buffer entry points (end-to-end path: pinned staging + chunked H2D/compute/D2H overlap) ------- */
 /* h_dU = alpha*scale*D*h_U + beta*h_dU for host arrays; copies are pipelined in chunks of
  * `chunk_instances` (0 = auto) over three streams.  This is what `mul!(dU::Matrix, D, U::Matrix)` on

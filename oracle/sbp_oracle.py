@@ -775,3 +775,134 @@ def solve_lowstorage_3sp(rhs, u0, t0, t1, dt0, tab, adaptive=True, abstol=1e-6, 
             nrej += 1
             dt = h * q
     return u, nacc, nrej, times
+
+
+# --------------------------------------------------------------------------------------
+# Construction objective: literal restatement of ext/utils.jl:26-148,164-190 and of the two objective functions
+# --------------------------------------------------------------------------------------
+
+
+def _set_skew_symmetric(M, sigma, k):
+    """ext/utils.jl:26-37 (k: 0-based position in sigma; returns the next position)."""
+    n = M.shape[0]
+    for i in range(n):
+        for j in range(i + 1, n):
+            M[i, j] = sigma[k]
+            M[j, i] = -sigma[k]
+            k += 1
+    return k
+
+
+def _set_banded(Dm, sigma, bandwidth, init_k, different_values):
+    """ext/utils.jl:40-58."""
+    n = Dm.shape[0]
+    k = init_k
+    for i in range(n):
+        for j in range(i + 1, n):
+            if j - i <= bandwidth:
+                if different_values:
+                    l = k
+                    k += 1
+                else:
+                    l = init_k + (j - i) - 1
+                Dm[i, j] = sigma[l]
+                Dm[j, i] = -sigma[l]
+    return k
+
+
+def _set_triangular(Cm, sigma, bandwidth, size_boundary, init_k, different_values):
+    """ext/utils.jl:60-81 (1-based loops of the reference kept, indices shifted on access)."""
+    n = Cm.shape[0]
+    k = init_k + 1  # 1-based like the reference
+    start_i = n - bandwidth + 1 if different_values else size_boundary - bandwidth + 1
+    for i in range(start_i, n + 1):
+        for j in range(1, i - start_i + 2):
+            l = k if different_values else (init_k + 1) - 1 + bandwidth + j - (i - start_i + 1)
+            Cm[i - 1, j - 1] = sigma[l - 1]
+            k += 1
+    return k - 1
+
+
+def set_S(sigma, N, bandwidth=None, size_boundary=None, different_values=True, sparsity_pattern=None):
+    """set_S! / set_S_block_banded! / set_S_sparsity_pattern! (ext/utils.jl:83-148)."""
+    sigma = np.asarray(sigma, dtype=np.float64)
+    b = N - 1 if bandwidth is None else bandwidth
+    c = 2 * b if size_boundary is None else size_boundary
+    S = np.zeros((N, N))
+    if sparsity_pattern is not None:
+        k = 0
+        for i in range(N):
+            for j in range(i + 1, N):
+                if sparsity_pattern[i, j]:
+                    S[i, j] = sigma[k]
+                    S[j, i] = -sigma[k]
+                    k += 1
+        return S
+    if b == N - 1:
+        _set_skew_symmetric(S, sigma, 0)
+        return S
+    M1 = S[:c, :c]
+    k = _set_skew_symmetric(M1, sigma, 0)
+    M2 = S[N - c:, N - c:]
+    if different_values:
+        k = _set_skew_symmetric(M2, sigma, k)
+    else:
+        M2[:] = -M1[::-1, ::-1]
+    Dm = S[c:N - c, c:N - c]
+    k = _set_banded(Dm, sigma, b, k, different_values)
+    C1 = S[:c, c:N - c]
+    k = _set_triangular(C1, sigma, b, c, k, different_values)
+    S[c:N - c, :c] = -C1.T
+    C2 = S[c:N - c, N - c:]
+    if different_values:
+        k = _set_triangular(C2, sigma, b, c, k, different_values)
+        S[N - c:, c:N - c] = -C2.T
+    else:
+        C1_bar = C1[::-1, ::-1]
+        C2[:] = C1_bar.T
+        S[N - c:, c:N - c] = -C1_bar
+    return S
+
+
+def _sig(x):
+    return 1.0 / (1.0 + np.exp(-x))  # ext/utils.jl:153
+
+
+def create_P_diag(rho, vol):
+    """create_P (ext/utils.jl:164-168): diagonal of P."""
+    p = _sig(np.asarray(rho, dtype=np.float64))
+    return p * (vol / np.sum(p))
+
+
+def objective_function_space_operator(x, L, x_length, V, V_x, R, **structure):
+    """optimization_function_function_space_operator (ext/function_space_operators_optim.jl:89-105)."""
+    x = np.asarray(x, dtype=np.float64)
+    N = V.shape[0]
+    sigma, rho = x[:L], x[L:]
+    S = set_S(sigma, N, **structure)
+    A = S @ V - create_P_diag(rho, x_length)[:, None] * V_x + R
+    return float(np.sum(A * A))
+
+
+def objective_multidimensional(x, Ls, vol, normals, moments, boundary_indices, V, V_xis, corners=None, structures=None):
+    """optimization_function_multidimensional_function_space_operator
+    (ext/multidimensional_function_space_operators.jl:124-161); boundary_indices 0-based, corners: per direction the (0-based)
+    positions of the boundary entries that set_B! skips."""
+    x = np.asarray(x, dtype=np.float64)
+    d, N, Nb = len(V_xis), V.shape[0], len(normals)
+    offs = np.concatenate([[0], np.cumsum(Ls)])
+    rho, phi = x[len(x) - N - Nb:len(x) - Nb], x[len(x) - Nb:]
+    P = create_P_diag(rho, vol)
+    corners = corners if corners is not None else tuple([] for _ in range(d))
+    res = 0.0
+    for i in range(d):
+        S = set_S(x[offs[i]:offs[i + 1]], N, **(structures[i] if structures else {}))
+        b = np.zeros(N)
+        for j, k in enumerate(boundary_indices):  # set_B! (ext/utils.jl:179-190)
+            if j not in corners[i]:
+                b[k] = phi[j] * normals[j][i]
+        BV = b[:, None] * V
+        A = S @ V - P[:, None] * V_xis[i] + 0.5 * BV
+        Cm = V.T @ BV - moments[i]
+        res += np.sum(A * A) + np.sum(Cm * Cm)
+    return float(res)

@@ -26,6 +26,7 @@ from .conservation_laws import (AnalysisCallback, LowStorage3SpTableau,
                                 analyze_quantities, quantities, semidiscretize, solve_lowstorage_3sp,
                                 solve_ssprk53, step_schedule, tstops)
 from .container import load_operator, save_operator
+from .objective import ConstructionObjective, get_nsigma, skew_index_map
 from .sharding import shard_range
 
 __version__ = "0.1.0"

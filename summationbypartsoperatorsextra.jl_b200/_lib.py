@@ -110,6 +110,10 @@ SIGNATURES = {
     "sbp_solve_3sp_fsal": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_dbl, c_dbl, c_dbl, c_i32, c_dbl, c_dbl,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i64, c_void_p]),
     "sbp_error_norm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_dbl, c_dbl, P(c_dbl)]),
+    "sbp_objective_create": (c_i32, [c_void_p, c_i32, c_i32, c_i32, c_i32, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_dbl, P(c_void_p)]),
+    "sbp_objective_eval": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "sbp_objective_destroy": (c_i32, [c_void_p]),
 }
 
 

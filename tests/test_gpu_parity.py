@@ -818,6 +818,58 @@ def test_block_sparse_kernels_are_deterministic(ctx, organisation):
         assert rel_err(first[b], semio.rhs(U[b], 0.3)) <= TOL
 
 
+# ---- f4: batched construction objective ------------------------------------------------------------------------------
+@pytest.mark.parametrize("structure", [dict(), dict(bandwidth=2, size_boundary=4), dict(bandwidth=3, size_boundary=6, different_values=False),
+                                       "sparsity"])
+def test_construction_objective_1d(ctx, structure):
+    """optimization_function_function_space_operator (ext/function_space_operators_optim.jl:89-105) for a population of
+    candidates in one launch, against the oracle's per-candidate restatement."""
+    rng = np.random.default_rng(3)
+    N, K = 21, 5
+    nodes = np.linspace(0.0, 1.0, N)
+    V = np.stack([nodes**k for k in range(K)], axis=1) * rng.uniform(0.5, 1.5, K)
+    Vx = np.stack([k * nodes ** max(k - 1, 0) if k else np.zeros(N) for k in range(K)], axis=1)
+    Bm = np.zeros((N, N))
+    Bm[0, 0], Bm[-1, -1] = -1.0, 1.0
+    R = Bm @ V / 2
+    if structure == "sparsity":
+        pat = np.triu(rng.random((N, N)) < 0.25, 1)
+        kw = dict(sparsity_pattern=pat)
+    else:
+        kw = dict(structure)
+    L = S.get_nsigma(N, **kw)
+    obj = S.ConstructionObjective(ctx, V, [Vx], 1.0, [S.skew_index_map(N, **kw)], R=R)
+    X = np.concatenate([rng.normal(size=(300, L)), rng.normal(size=(300, N))], axis=1)
+    f = obj.evaluate(X)
+    ref = np.array([O.objective_function_space_operator(x, L, 1.0, V, Vx, R, **kw) for x in X])
+    assert np.max(np.abs(f - ref) / ref) <= 1e-12
+    obj.close()
+
+
+def test_construction_objective_multidimensional(ctx):
+    """optimization_function_multidimensional_function_space_operator
+    (ext/multidimensional_function_space_operators.jl:124-161) incl. the boundary operator with corners and the moment term."""
+    rng = np.random.default_rng(4)
+    D2 = S.tensor_product_operator_2D(S.mattsson_nordstrom_2004(2, -1.0, 1.0, 5))
+    N, K = D2.N, 4
+    x, y = D2.grid[:, 0], D2.grid[:, 1]
+    V = np.stack([np.ones(N), x, y, x * y], axis=1)
+    Vxs = [np.stack([np.zeros(N), np.ones(N), np.zeros(N), y], axis=1), np.stack([np.zeros(N), np.zeros(N), np.ones(N), x], axis=1)]
+    Ms = [rng.normal(size=(K, K)) for _ in range(2)]
+    pats = [np.triu(rng.random((N, N)) < 0.2, 1) for _ in range(2)]
+    maps = [S.skew_index_map(N, sparsity_pattern=p) for p in pats]
+    Ls = [S.get_nsigma(N, sparsity_pattern=p) for p in pats]
+    Nb = len(D2.boundary_indices)
+    obj = S.ConstructionObjective(ctx, V, Vxs, 4.0, maps, moments=Ms, normals=D2.normals, boundary_indices=D2.boundary_indices,
+                                  corners=D2.corners)
+    X = rng.normal(size=(257, sum(Ls) + N + Nb))
+    f = obj.evaluate(X)
+    ref = np.array([O.objective_multidimensional(xx, Ls, 4.0, D2.normals, Ms, D2.boundary_indices, V, Vxs, corners=D2.corners,
+                                                 structures=[dict(sparsity_pattern=p) for p in pats]) for xx in X])
+    assert np.max(np.abs(f - ref) / ref) <= 1e-12
+    obj.close()
+
+
 # ---- full-size configurations through size-independent properties ---------------------------------------------------
 def test_config2_full_size_properties(ctx):
     """BASELINE config 2 at full size (N = 64, B = 2^20): instances are tiled copies of 2048 distinct vectors, so the

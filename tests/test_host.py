@@ -325,3 +325,21 @@ def test_julia_shim_ccall_signatures():
         assert need in seen, f"the Julia shim does not bind {need}"
     # a batch is not an AbstractMatrix (generic fallbacks must not apply) and operators / buffers are released by the context
     assert "DeviceBatch <: AbstractMatrix" not in src and "finalizer(close, ctx)" in src
+
+
+def test_construction_index_maps_match_the_reference_set_S():
+    """f4: the index map the device objective is built from equals what the oracle's literal restatement of set_S!
+    (ext/utils.jl:83-148) writes for sigma = (1, ..., L), for every structure; get_nsigma (src/utils/optimization.jl:15-43)."""
+    import sbp_b200 as S
+    from oracle import sbp_oracle as O
+
+    for (N, b, c, dv) in [(9, None, None, True), (14, 2, 4, True), (14, 2, 4, False), (15, 3, 6, True), (15, 3, 6, False),
+                          (13, 2, 5, True), (12, 1, 2, False), (101, 3, 6, True)]:
+        L = S.get_nsigma(N, b, c, dv)
+        M = S.skew_index_map(N, b, c, dv)
+        assert np.array_equal(M.astype(float), O.set_S(np.arange(1, L + 1, dtype=float), N, b, c, dv)), (N, b, c, dv)
+        assert np.max(np.abs(M)) == L and np.array_equal(M, -M.T)
+    pat = np.triu(np.random.default_rng(0).random((10, 10)) < 0.3, 1)
+    L = S.get_nsigma(10, sparsity_pattern=pat)
+    assert np.array_equal(S.skew_index_map(10, sparsity_pattern=pat).astype(float),
+                          O.set_S(np.arange(1, L + 1, dtype=float), 10, sparsity_pattern=pat))
