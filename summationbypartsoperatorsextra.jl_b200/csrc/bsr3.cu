@@ -125,7 +125,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     __shared__ int sem_fin[4];  // CW == 12, p.sem: chains finished per scheduler (at most two of its three warps multiply at a time)
     // XT: the extra operand of a fused stage update travels through the staging buffers (TMA loads issued by the helpers)
     const bool XT = HELP && FUSED && p.cb != 0.0;
-    static_assert(!HELP || (CW == kBsrCH && OUT == 2), "helper warps: 8 consumer warps with TMA output");
+    static_assert(!HELP || (CW == kBsrCH && OUT == 2 && kBsrCH % 4 == 0), "helper warps: one consumer warp per row block of a chunk, TMA output");
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
     int* s_pos = reinterpret_cast<int*>(s_val + (size_t)kB3FragStages * p.maxf * 32);  // kB3FragStages * maxf * PS
@@ -186,8 +186,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             int trh = 0;
 #endif
             const int4* rec = p.item;
-            int rowA[2], rowB[2];
-            for (int k = 0; k < 2; k++) {
+            constexpr int KH = kBsrCH / 4;  // consumer warps served by one helper (h, h + 4, ...)
+            int rowA[KH], rowB[KH];
+            for (int k = 0; k < KH; k++) {
                 const int4 a = __ldg(rec + 2 * (h + 4 * k));
                 rowA[k] = a.z, rowB[k] = a.w;
             }
@@ -200,20 +201,20 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 if (rA < N && rB < N) tma_load_2d(so + 8 * MT * 4, &tmap_ex, rB, y, &ext_full[w]);
             };
             if (XT && (long long)blockIdx.x < ntiles)
-                for (int k = 0; k < 2; k++) load_extra(h + 4 * k, rowA[k], rowB[k], (int)(blockIdx.x * TI));
+                for (int k = 0; k < KH; k++) load_extra(h + 4 * k, rowA[k], rowB[k], (int)(blockIdx.x * TI));
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
                 for (int cc = 0; cc < p.nch; cc++) {
                     const int cn = c + 1 < p.nch ? c + 1 : 0;
-                    int nA[2], nB[2];
-                    for (int k = 0; k < 2; k++) {  // next item's rows (the records repeat with the tile)
+                    int nA[KH], nB[KH];
+                    for (int k = 0; k < KH; k++) {  // next item's rows (the records repeat with the tile)
                         const int4 a = __ldg(rec + 2 * (kBsrCH * cn + h + 4 * k));
                         nA[k] = a.z, nB[k] = a.w;
                     }
                     // first tensor row of the next item (same tile, or this CTA's next tile); -1: there is none
                     const long long ntile = cc + 1 < p.nch ? tile : tile + gridDim.x;
                     const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
-                    for (int k = 0; k < 2; k++) {
+                    for (int k = 0; k < KH; k++) {
                         const int w = h + 4 * k;
                         mbar_wait(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
                         B3_TR(warp, trh, 2 * k);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
 #if SBP_B3_TRACE
                     trh++;
 #endif
-                    for (int k = 0; k < 2; k++) rowA[k] = nA[k], rowB[k] = nB[k];
+                    for (int k = 0; k < KH; k++) rowA[k] = nA[k], rowB[k] = nB[k];
                     c = cn;
                     ph ^= 1;
                 }
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     int ps = warp % kBsrCH, pc = (warp / kBsrCH) % p.nch;
     auto advance = [&]() {
         const int q = ps + CW;
-        ps = q & (kBsrCH - 1);
+        ps = q % kBsrCH;
         pc += q / kBsrCH;
         while (pc >= p.nch) pc -= p.nch;
     };
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         trit++;
 #endif
         skip = (myslot + CW) / kBsrCH - 1;
-        myslot = (myslot + CW) & (kBsrCH - 1);
+        myslot = (myslot + CW) % kBsrCH;
       } else {
         // no block of this item: observe its boxes (later windows reach back into them) and release it at once
         mbar_wait(&fbar_full[fst], fphase);
@@ -724,7 +725,7 @@ done:
 static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out, int cw) {
     const size_t ops = ((size_t)kB3FragStages * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
     // staging per consumer warp (TMA tensor stores only): 2 quads x instances x 4 rows
-    const size_t staging = out == 2 ? (size_t)(cw == 12 ? 12 : 8) * 2 * 8 * MT * 4 * 8 : 0;
+    const size_t staging = out == 2 ? (size_t)(cw == 12 ? 12 : kBsrCH) * 2 * 8 * MT * 4 * 8 : 0;
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;
 }
 static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int out, int cw) {
@@ -759,14 +760,14 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
 #define SBP_BSR3_OUT(S)                                                                                    \
     switch (out) {                                                                                         \
         case 2: return cw == 12 ? launch_bsr3_k<MT, S, 2, 12>(ctx, p, smem)                                \
-                          : cw == 9 ? launch_bsr3_k<MT, S, 2, 8, true>(ctx, p, smem)                       \
-                                    : launch_bsr3_k<MT, S, 2, 8>(ctx, p, smem);                            \
-        case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, 8>(ctx, p, smem); \
-        default: return launch_bsr3_k<MT, S, 0, 8>(ctx, p, smem);                                          \
+                          : cw == 9 ? launch_bsr3_k<MT, S, 2, kBsrCH, true>(ctx, p, smem)                  \
+                                    : launch_bsr3_k<MT, S, 2, kBsrCH>(ctx, p, smem);                       \
+        case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, kBsrCH>(ctx, p, smem); \
+        default: return launch_bsr3_k<MT, S, 0, kBsrCH>(ctx, p, smem);                                     \
     }
     if (p.fused) {  // stage updates: RHS launches with TMA output and store helpers (checked by launch_bsr3)
-        if (sat == 1) return launch_bsr3_k<MT, 1, 2, 8, true, true>(ctx, p, smem);
-        return launch_bsr3_k<MT, 2, 2, 8, true, true>(ctx, p, smem);
+        if (sat == 1) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, true>(ctx, p, smem);
+        return launch_bsr3_k<MT, 2, 2, kBsrCH, true, true>(ctx, p, smem);
     }
     if (sat == 1) { SBP_BSR3_OUT(1) }
     if (sat == 2) { SBP_BSR3_OUT(2) }
@@ -790,7 +791,7 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     if (enabled < 0 && !(out == 2 && (satmode != 0 || op->bsr_N != op->N || wide))) return false;
     const int forced_cw = ctx->tune[T_BSR_CW], help = ctx->tune[T_BSR_HELP];
     // cw: 8 consumer warps | 12 (SBP_BSR_CW=12) | 9 = 8 consumer warps + store helper warps (SBP_BSR_HELP=1, TMA output)
-    const int cw = (forced_cw == 12 && out != 0 && !p.fused) ? 12 : (help && out == 2) ? 9 : 8;
+    const int cw = (forced_cw == 12 && out != 0 && !p.fused && kBsrCH == 8) ? 12 : (help && out == 2) ? 9 : 8;
     // fused stage updates: helper variant of an RHS launch (the extra operand travels through the staging buffers: the
     // helpers fetch its quads by TMA as soon as the previous block's results have been read out)
     // (measured: 2D RHS N = 1296 0.362 ms per stage with the extra operand against 0.414 on k_bsr; 1D RHS N = 101 0.279 against
