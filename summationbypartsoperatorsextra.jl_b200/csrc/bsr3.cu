@@ -46,6 +46,14 @@
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
 
+#ifndef SBP_B3_PARKED
+#define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
+#endif
+#if SBP_B3_PARKED
+#define B3_PARK(bar, par) mbar_wait_parked(bar, par)
+#else
+#define B3_PARK(bar, par) mbar_wait(bar, par)
+#endif
 #ifndef SBP_B3_TRACE
 #define SBP_B3_TRACE 0  // 1: clock64 stamps of CTA 0 into a global buffer (sbp_debug_set_trace), tools/trace_bsr3.py draws the timeline
 #endif
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
                     for (int k = 0; k < KH; k++) {
                         const int w = h + 4 * k;
-                        mbar_wait(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
+                        B3_PARK(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
                         B3_TR(warp, trh, 2 * k);
                         if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
                         const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 int jb = 0, x = 0;  // boxes of this tile already requested, node coordinate of the next box
                 for (int c = 0; c < p.nch; c++) {
                     const int4 cmn = __ldg(p.chmeta + (c + 1 < p.nch ? c + 1 : 0));
-                    if (round > 0) mbar_wait(&pempty[st], (round - 1) & 1);
+                    if (round > 0) B3_PARK(&pempty[st], (round - 1) & 1);
                     B3_TR(warp, trp, 0);
                     const uint32_t bar = full32 + 8u * st;
                     if (boxes) {

@@ -81,6 +81,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// wait of a thread that has nothing else to do (TMA producers, store helpers): try_wait with a suspend-time hint, so that the
+// thread sleeps in hardware until the phase completes (or `ns` nanoseconds pass) instead of re-issuing a poll every few cycles
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 20000) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+}
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes multiple of 16, 16-B aligned)
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(
