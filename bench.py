@@ -719,12 +719,13 @@ def run_native(args):
     achieved = dofs_step * BYTES_PER_DOF / kernel_ms / 1e6  # GB/s
     fp64_dmma, fp64_dfma = fp64_peak()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("config2_dense_small_bytes_per_launch")
-        except Exception:
-            traffic = None
+    for tp in (os.path.join(ROOT, "profiles", "r2_traffic.json"), os.path.join(ROOT, "profiles", "r1_traffic.json")):
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("config2_dense_small_bytes_per_launch")
+                break
+            except Exception:
+                traffic = None
     kern = op.info()["kernel"]
     line = {
         "metric": "GDOF/s (batched SBP operator apply, Float64)",
