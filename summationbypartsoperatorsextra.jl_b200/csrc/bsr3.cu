@@ -29,7 +29,7 @@
 #include <algorithm>
 #include "bsr.cuh"
 
-// -DSBP_B3_EXP=n: what-if builds for bottleneck hunting (WRONG RESULTS): 1 = no DMMA, 2 = no A-operand loads inside the chain,
+// -DSBP_B3_EXP=n: what-if builds for bottleneck hunting (WRONG RESULTS; 4 deadlocks with the store-helper warps): 1 = no DMMA, 2 = no A-operand loads inside the chain,
 // 3 = no TMA box loads, 4 = no output, 5 = all tiles store to the rows of tile 0, 6 = all tiles load the rows of tile 0, 10 = no proxy fence before the TMA stores
 // (7 = staging + fence but no TMA store, 8 = TMA stores without staging/fence, 9 = accumulators consumed + fence, no stores:
 // measured in session 4, code removed)
@@ -83,6 +83,10 @@ constexpr int kB3Stages = 4;      // box stages (mbarrier pairs)
 #define SBP_B3_FSTAGES 2
 #endif
 constexpr int kB3FragStages = SBP_B3_FSTAGES;  // operator-fragment stages
+#ifndef SBP_B3_MERGED
+#define SBP_B3_MERGED 0  // 1: boxes and operator fragments of an item complete ONE full barrier (both producers arrive on it) and
+#endif                   // share the empty barrier: one mbarrier wait per item instead of two.  Measured: config 3 0.2898 either way.
+constexpr bool kB3Merged = SBP_B3_MERGED != 0;
 
 // shared-memory loads at a 32-bit shared address + compile-time offset (volatile: they keep their place in the software pipeline)
 template <uint32_t OFF>
@@ -136,9 +140,10 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     static_assert(!HELP || (CW == kBsrCH && OUT == 2 && kBsrCH % 4 == 0), "helper warps: one consumer warp per row block of a chunk, TMA output");
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
-    int* s_pos = reinterpret_cast<int*>(s_val + (size_t)kB3FragStages * p.maxf * 32);  // kB3FragStages * maxf * PS
+    const int fs = kB3Merged ? p.nst : kB3FragStages;                                 // fragment stages
+    int* s_pos = reinterpret_cast<int*>(s_val + (size_t)fs * p.maxf * 32);            // fs * maxf * PS
     // output staging, per consumer warp: [quad A | quad B][8 * MT instances][4 rows]  (128-byte aligned)
-    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)kB3FragStages * p.maxf * PS + 31) & ~(size_t)31));
+    double* s_out = reinterpret_cast<double*>(s_pos + (((size_t)fs * p.maxf * PS + 31) & ~(size_t)31));
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler
     const int N = p.N, nst = p.nst, nbox = p.nbox;
     const long long ntiles = (p.B + TI - 1) / TI;
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     const bool alpha_m1 = p.alpha == -1.0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; s++) {
-            mbar_init(&bar_full[s], 1);      // the box producer's arrive.expect_tx
+            mbar_init(&bar_full[s], kB3Merged ? 2 : 1);  // the box producer's arrive.expect_tx (+ the fragment producer's)
             mbar_init(&bar_empty[s], CONS);  // lane 0 of EVERY consumer warp, block in this item or not: a stage that could be
         }                                    // refilled without a warp's arrival might lap that warp's phase tracking
         for (int s = 0; s < kB3FragStages; s++) {
@@ -254,9 +259,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // ------- producers (as in bsr.cu): warp CONS requests the boxes of the batch, warp CONS + 1 the operator fragments -------
         if (lane == 0) {
             const bool boxes = warp == CONS;
-            const int pst = boxes ? nst : kB3FragStages;  // stages of this producer's barrier set
-            uint64_t* const pfull = boxes ? bar_full : fbar_full;
-            uint64_t* const pempty = boxes ? bar_empty : fbar_empty;
+            const int pst = (boxes || kB3Merged) ? nst : kB3FragStages;  // stages of this producer's barrier set
+            uint64_t* const pfull = (boxes || kB3Merged) ? bar_full : fbar_full;
+            uint64_t* const pempty = (boxes || kB3Merged) ? bar_empty : fbar_empty;
             int st = 0, round = 0, slot = 0;
 #if SBP_B3_TRACE
             int trp = 0;
@@ -297,7 +302,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                             if (++slot == nbox) slot = 0;
                         }
                     } else {
-                        const unsigned nfr = (unsigned)(cm.y - cm.x);
+                        // what-if 13 (WRONG RESULTS): operator fragments are fetched for the CTA's first tile only
+                        const unsigned nfr = (SBP_B3_EXP == 13 && tile != (long long)blockIdx.x) ? 0u : (unsigned)(cm.y - cm.x);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
                                      "r"(nfr * (256u + 4u * PS))
                                      : "memory");
@@ -482,7 +488,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         const bool work = active && nf > 0;
         // the operator fragments arrive ahead of the boxes: the first B operand and the ring addresses of the first two
         // fragments are fetched before the wait for the boxes
-        mbar_wait(&fbar_full[fst], fphase);
+        if (kB3Merged) mbar_wait(&bar_full[st], phase);
+        else mbar_wait(&fbar_full[fst], fphase);
         B3_TR(warp, trit, 1);
         double b0v = 0.0;
         uint32_t adr0 = su32, adr = su32;
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             adr0 = conv(lds32<0>(sp));
             adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
         }
-        mbar_wait(&bar_full[st], phase);
+        if (!kB3Merged) mbar_wait(&bar_full[st], phase);
         B3_TR(warp, trit, 2);
         if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
         if (CW == 12 && p.sem) {  // block sem_n of this scheduler may multiply once sem_n - p.sem + 1... of its predecessors have finished
@@ -641,7 +648,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(&bar_empty[st]);    // the ring slots behind this item's window may be refilled
-            mbar_arrive(&fbar_empty[fst]);  // and so may the fragment buffers
+            if (!kB3Merged) mbar_arrive(&fbar_empty[fst]);  // and so may the fragment buffers
         }
         B3_TR(warp, trit, 5);
 
@@ -700,11 +707,11 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         myslot = (myslot + CW) % kBsrCH;
       } else {
         // no block of this item: observe its boxes (later windows reach back into them) and release it at once
-        mbar_wait(&fbar_full[fst], fphase);
+        if (!kB3Merged) mbar_wait(&fbar_full[fst], fphase);
         mbar_wait(&bar_full[st], phase);
         if (lane == 0) {
             mbar_arrive(&bar_empty[st]);
-            mbar_arrive(&fbar_empty[fst]);
+            if (!kB3Merged) mbar_arrive(&fbar_empty[fst]);
         }
         skip--;
       }
@@ -716,9 +723,12 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             offB += stepBr;
             offB = min(offB, offB - ringBr);
         }
-        if (++st == nstr) st = 0, phase ^= 1;
         svst += stvalB, spst += stposB;
-        if (++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
+        if (++st == nstr) {
+            st = 0, phase ^= 1;
+            if (kB3Merged) svst = sval32, spst = spos32;
+        }
+        if (!kB3Merged && ++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
      }
     }
 done:
@@ -731,7 +741,7 @@ done:
 }
 
 static size_t bsr3_smem(const sbp_op* op, int MT, int D, int out, int cw) {
-    const size_t ops = ((size_t)kB3FragStages * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
+    const size_t ops = ((size_t)(kB3Merged ? D + 1 : kB3FragStages) * op->bsr_maxf * (32 * 8 + 4 * 4) + 127) & ~(size_t)127;
     // staging per consumer warp (TMA tensor stores only): 2 quads x instances x 4 rows
     const size_t staging = out == 2 ? (size_t)(cw == 12 ? 12 : kBsrCH) * 2 * 8 * MT * 4 * 8 : 0;
     return (size_t)op->bsr_nbox[D] * 8 * MT * kBsrBX * 8 + ops + staging;

@@ -78,6 +78,8 @@ def main():
     ap.add_argument("--first", type=int, default=40)
     ap.add_argument("--count", type=int, default=2)
     ap.add_argument("--cw", type=int, default=8, help="consumer warps of the traced configuration (8 or 12)")
+    ap.add_argument("--lockstep", action="store_true", help="12 consumer warps with chunks of 12 (-DSBP_BSR_CH=12): a block per warp and item")
+    ap.add_argument("--nch", type=int, default=21, help="chunks per tile (21 for config 3 with chunks of 8, 14 with chunks of 12)")
     args = ap.parse_args()
     ctx = S.Context(0)
     for kv in filter(None, args.opts.split(",")):
@@ -95,17 +97,18 @@ def main():
         semi(du, u, None, 0.1)
     ctx.synchronize()
     T = buf.to_host(np.int64, 32 * NI * 8).reshape(32, NI, 8)
-    if args.cw != 8:
+    if args.cw != 8 and not args.lockstep:
         return stats_free_running(T, args.cw)
-    cons = T[:8]
+    NC = args.cw
+    cons = T[:NC]
     t0 = cons[:, args.first, 0].min()
     names = ["top", "frag", "box", "c0", "c1", "rel", "free", "stg"]
     print("consumer warps, items", args.first, "..", args.first + args.count - 1, "(cycles relative to the first stamp)")
     for it in range(args.first, args.first + args.count):
-        for w in range(8):
+        for w in range(NC):
             print(f"  item {it} warp {w}: " + " ".join(f"{n}={cons[w, it, k] - t0:6d}" for k, n in enumerate(names)))
     # statistics over items 21..83 (three whole tiles of 21 chunks for config 3)
-    lo, hi = 21, 84
+    lo, hi = args.nch, 4 * args.nch
     sl = slice(lo, hi)
     valid = (cons[:, sl, 3] > 0) & (cons[:, sl, 4] > 0)  # blocks that multiplied (padding records of a tile's last chunk do not)
 
@@ -123,7 +126,7 @@ def main():
     # how many warps of a scheduler are inside their chain at the same time
     t_begin, t_end = cons[:, lo, 0].min(), cons[:, hi, 0].max()
     for s_ in range(4):
-        ws = [w for w in range(8) if w % 4 == s_]
+        ws = [w for w in range(NC) if w % 4 == s_]
         ev = []
         for w in ws:
             for it in range(lo, hi):
@@ -131,28 +134,28 @@ def main():
                     ev.append((cons[w, it, 3], 1))
                     ev.append((cons[w, it, 4], -1))
         ev.sort()
-        lvl, last, hist = 0, t_begin, {0: 0, 1: 0, 2: 0}
+        lvl, last, hist = 0, t_begin, {0: 0, 1: 0, 2: 0, 3: 0}
         for t, dlt in ev:
             hist[lvl] += t - last
             lvl += dlt
             last = t
         hist[0] += t_end - last
         tot = sum(hist.values())
-        print(f"scheduler {s_}: chains in flight 0: {100 * hist[0] / tot:.0f}%  1: {100 * hist[1] / tot:.0f}%  2: {100 * hist[2] / tot:.0f}%")
+        print(f"scheduler {s_}: chains in flight " + "  ".join(f"{k}: {100 * hist[k] / tot:.0f}%" for k in range(4)))
     # per chunk of the tile: when do the boxes arrive relative to the moment the LAST warp is ready for them?
     print("chunk: mean over 3 tiles of (box-ready - fragments-ready) of the last warp, chain length, release spread")
-    for c in range(21):
-        its = [lo + c + 21 * k for k in range(3)]
+    for c in range(args.nch):
+        its = [lo + c + args.nch * k for k in range(3)]
         wait = np.mean([(cons[:, it, 2] - cons[:, it, 1]).min() for it in its])
-        chain = np.mean([np.mean([cons[w, it, 4] - cons[w, it, 3] for w in range(8) if cons[w, it, 3] > 0]) for it in its])
+        chain = np.mean([np.mean([cons[w, it, 4] - cons[w, it, 3] for w in range(NC) if cons[w, it, 3] > 0]) for it in its])
         rel = np.mean([cons[:, it, 5].max() - cons[:, it, 5].min() for it in its])
         per = np.mean([cons[:, it + 1, 0].mean() - cons[:, it, 0].mean() for it in its])
         print(f"  chunk {c:2d}: min box wait {wait:6.0f}  chain {chain:6.0f}  release spread {rel:6.0f}  item period {per:6.0f}")
-    prod = T[8]
+    prod = T[NC]
     print("box producer: stage free -> requests issued mean %.0f cycles; then waits %.0f for the next free stage" %
           ((prod[sl, 1] - prod[sl, 0]).mean(), (prod[lo + 1:hi + 1, 0] - prod[sl, 1]).mean()))
     for h in range(4):
-        hp = T[10 + h]
+        hp = T[NC + 2 + h]
         print(f"helper {h}: full->stored warp {h}: %.0f, warp {h + 4}: %.0f" % ((hp[sl, 1] - hp[sl, 0]).mean(), (hp[sl, 3] - hp[sl, 2]).mean()))
 
 
