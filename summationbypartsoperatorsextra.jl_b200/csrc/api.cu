@@ -565,6 +565,21 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
                 e[2] = 1 << 30, e[3] = (1 << 30) + 4;
             }
         }
+    if (const char* e = getenv("SBP_BSR_STATS"); e && *e == '1') {  // debug aid (operator creation, not a launch path)
+        long long slot[CH] = {}, sched[4] = {}, sum_max = 0;
+        for (int c = 0; c < nch; c++) {
+            long long sc[4] = {};
+            for (int k = 0; k < CH; k++)
+                if (c * CH + k < nrb) slot[k] += rbmeta[4 * (c * CH + k) + 1], sc[k & 3] += rbmeta[4 * (c * CH + k) + 1];
+            for (int q = 0; q < 4; q++) sched[q] += sc[q];
+            sum_max += *std::max_element(sc, sc + 4);
+        }
+        fprintf(stderr, "bsr stats: N %d, %d row blocks, %d chunks, %lld fragments (%.2f per block), max per block %d\n  per slot:", N, nrb,
+                nch, (long long)frag.size() / 32, (double)(frag.size() / 32) / nrb, maxnf);
+        for (int k = 0; k < CH; k++) fprintf(stderr, " %lld", slot[k]);
+        fprintf(stderr, "\n  per scheduler: %lld %lld %lld %lld, sum over chunks of the busiest scheduler %lld (mean %.1f)\n", sched[0], sched[1],
+                sched[2], sched[3], sum_max, (double)(frag.size() / 32) / 4);
+    }
     op->bsr_maxf = maxf;
     op->bsr_nrb = nrb;
     op->bsr_rows = rows;

@@ -46,6 +46,14 @@
 #define SBP_B3_DEFER 0  // 1: deferred epilogue (see k_bsr3); measured: config 3 0.344 ms vs 0.329 without
 #endif
 
+#ifndef SBP_B3_RECPOS
+#define SBP_B3_RECPOS 0  // where a consumer warp requests the record of its next row block: 0 = at the top of the item, 1 = after its chain
+                         // (measured: 1 is 1-3 % slower on config 3)
+#endif
+#ifndef SBP_B3_GATE
+#define SBP_B3_GATE 0  // k > 0: staggered chains -- a consumer warp starts its chain only while the other warp of its scheduler is not
+#endif                 // inside the first k/8 of its own (shared-memory gate per scheduler); 0: free running.  Measured: k = 3..6 cost
+                       // 8 % on config 3 (0.324-0.328 vs 0.299 ms in the same build), 6-13 % without any memory traffic
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -87,6 +95,13 @@ constexpr int kB3FragStages = SBP_B3_FSTAGES;  // operator-fragment stages
 #define SBP_B3_MERGED 0  // 1: boxes and operator fragments of an item complete ONE full barrier (both producers arrive on it) and
 #endif                   // share the empty barrier: one mbarrier wait per item instead of two.  Measured: config 3 0.2898 either way.
 constexpr bool kB3Merged = SBP_B3_MERGED != 0;
+// what-ifs that keep the tensor work (ptxas deletes an mma.sync whose accumulators are never read, "asm volatile" or not: the
+// "no output" build 4 measures a kernel with 2/7 of its DMMAs; check `cuobjdump -sass | grep -c DMMA` of every what-if build)
+constexpr bool kNoLoads = SBP_B3_EXP == 3 || SBP_B3_EXP == 31 || SBP_B3_EXP >= 32;   // no TMA box loads
+constexpr bool kNoStores = SBP_B3_EXP == 30 || SBP_B3_EXP == 31 || SBP_B3_EXP >= 32;  // helpers skip the TMA stores
+constexpr bool kFragsOnce = SBP_B3_EXP == 13 || SBP_B3_EXP >= 32;                     // fragments fetched for the first tile only
+constexpr bool kNoCodes = SBP_B3_EXP == 40 || SBP_B3_EXP == 41 || SBP_B3_EXP == 43;   // ring addresses do not depend on loaded codes
+constexpr bool kNoOperands = SBP_B3_EXP == 2 || SBP_B3_EXP == 41 || SBP_B3_EXP == 42;  // one A operand per fragment comes from a register
 
 // shared-memory loads at a 32-bit shared address + compile-time offset (volatile: they keep their place in the software pipeline)
 template <uint32_t OFF>
@@ -131,9 +146,18 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     extern __shared__ __align__(128) double smem[];
     // boxes and operator fragments have separate stage counts: p.nst box stages (HBM latency: as deep as the ring allows),
     // kB3FragStages fragment stages (L2 latency: two are enough, each costs maxf * 272 bytes)
-    __shared__ uint64_t bar_full[kB3Stages], bar_empty[kB3Stages], fbar_full[kB3FragStages], fbar_empty[kB3FragStages];
-    __shared__ uint64_t out_full[kBsrCH], out_empty[kBsrCH];  // HELP: staging buffer of consumer warp w filled / stored
-    __shared__ uint64_t ext_full[kBsrCH];  // HELP + FUSED: the quads of `extra` for the warp's next block are in its staging buffer
+    // all mbarriers in one array: a consumer warp addresses them as (one pinned 32-bit shared address) + constant
+    constexpr int O_FULL = 0, O_EMPTY = O_FULL + kB3Stages, O_FFULL = O_EMPTY + kB3Stages, O_FEMPTY = O_FFULL + kB3FragStages;
+    constexpr int O_OFULL = O_FEMPTY + kB3FragStages, O_OEMPTY = O_OFULL + kBsrCH, O_XFULL = O_OEMPTY + kBsrCH;
+    __shared__ uint64_t bars[O_XFULL + kBsrCH];
+    uint64_t* const bar_full = bars + O_FULL;
+    uint64_t* const bar_empty = bars + O_EMPTY;
+    uint64_t* const fbar_full = bars + O_FFULL;
+    uint64_t* const fbar_empty = bars + O_FEMPTY;
+    uint64_t* const out_full = bars + O_OFULL;    // HELP: staging buffer of consumer warp w filled / stored
+    uint64_t* const out_empty = bars + O_OEMPTY;
+    uint64_t* const ext_full = bars + O_XFULL;    // HELP + FUSED: the quads of `extra` for the warp's next block are in its staging buffer
+    __shared__ int gate[4];     // SBP_B3_GATE: id of the warp inside the gated part of its chain, -1: open
     __shared__ int sem_fin[4];  // CW == 12, p.sem: chains finished per scheduler (at most two of its three warps multiply at a time)
     // XT: the extra operand of a fused stage update travels through the staging buffers (TMA loads issued by the helpers)
     const bool XT = HELP && FUSED && p.cb != 0.0;
@@ -163,7 +187,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             mbar_init(&out_empty[s], 1);
             mbar_init(&ext_full[s], 1);
         }
-        for (int s = 0; s < 4; s++) sem_fin[s] = 0;
+        for (int s = 0; s < 4; s++) sem_fin[s] = 0, gate[s] = -1;
         mbar_fence_init();
     }
     __syncthreads();
@@ -233,7 +257,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         B3_TR(warp, trh, 2 * k);
                         if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
                         const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
-                        if (rowA[k] < N) {
+                        if (rowA[k] < N && !kNoStores) {
                             tma_store_2d(&tmap_out, rowA[k], b0, so);
                             if (rowB[k] < N) tma_store_2d(&tmap_out, rowB[k], b0, so + 8 * MT * 4);
                             bulk_commit();
@@ -280,9 +304,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (boxes) {
                         const int jn = cm.w;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
-                                     "r"(SBP_B3_EXP == 3 ? 0u : (unsigned)(jn - jb) * BOXB)
+                                     "r"(kNoLoads ? 0u : (unsigned)(jn - jb) * BOXB)
                                      : "memory");
-                        if (SBP_B3_EXP == 3) jb = jn;
+                        if (kNoLoads) jb = jn;
                         for (; jb < jn; jb++, x += BX) {
                             if (p.pf > 0) {  // L2 prefetch of the box p.pf positions ahead in this CTA's box stream (HBM -> L2, no
                                 int jp = jb + p.pf;  // shared memory): the ring's lookahead is shallower than the HBM latency needs
@@ -303,7 +327,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         }
                     } else {
                         // what-if 13 (WRONG RESULTS): operator fragments are fetched for the CTA's first tile only
-                        const unsigned nfr = (SBP_B3_EXP == 13 && tile != (long long)blockIdx.x) ? 0u : (unsigned)(cm.y - cm.x);
+                        const unsigned nfr = (kFragsOnce && tile != (long long)blockIdx.x) ? 0u : (unsigned)(cm.y - cm.x);
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
                                      "r"(nfr * (256u + 4u * PS))
                                      : "memory");
@@ -351,10 +375,12 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         double2 sb;  // 2D SAT coefficients of the lane's two rows (0: none)
     };
     const double2* const sbs = reinterpret_cast<const double2*>(p.rb_bdiag) + t;
+    const int4* item_p = p.item;  // (pinned: one LDC.64 + its latency per item otherwise)
+    asm volatile("" : "+l"(item_p));
     auto load_rec = [&](int rb) {  // rb = 8 * chunk + slot
         Rec r;
-        r.a = __ldg(p.item + 2 * rb);
-        r.b = __ldg(p.item + 2 * rb + 1);
+        r.a = __ldg(item_p + 2 * rb);
+        r.b = __ldg(item_p + 2 * rb + 1);
         r.sb = make_double2(0.0, 0.0);
         if (SAT == 1) r.sb = __ldg(sbs + 4 * rb);
         return r;
@@ -366,12 +392,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     const uint32_t stepB = (uint32_t)stepb * BOXB;
     const int ntl = (int)ntiles, tstep = gridDim.x * TI, Bi = (int)p.B;
     // position of a warp's next row block in the (periodic) record array: chunk pc, slot ps; the one after it is CW blocks on
+    const int nch_p = __shfl_sync(0xffffffffu, p.nch, 0), grid_p = __shfl_sync(0xffffffffu, (int)gridDim.x, 0);  // pinned (see below)
     int ps = warp % kBsrCH, pc = (warp / kBsrCH) % p.nch;
     auto advance = [&]() {
         const int q = ps + CW;
         ps = q % kBsrCH;
         pc += q / kBsrCH;
-        while (pc >= p.nch) pc -= p.nch;
+        while (pc >= nch_p) pc -= nch_p;
     };
     Rec r0 = load_rec(kBsrCH * pc + ps);
     advance();
@@ -387,9 +414,14 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     uint32_t sval32 = smem_u32(s_val) + lane * 8, spos32 = smem_u32(s_pos) + t * 4;  // stage 0, this lane
     uint32_t stvalB = (uint32_t)p.maxf * 256u, stposB = (uint32_t)p.maxf * (4u * PS);
     asm volatile("" : "+r"(sgn), "+r"(su32), "+r"(ringBr), "+r"(sval32), "+r"(spos32), "+r"(stvalB), "+r"(stposB));
+    // barrier addresses: the array base and this warp's entry of the per-warp barriers
+    uint32_t bar32 = smem_u32(bars), wbar32 = smem_u32(bars + warp);
+    int lane_p = lane;  // (pinned as well: threadIdx.x would be re-read through S2R at every `lane == 0`)
+    asm volatile("" : "+r"(bar32), "+r"(wbar32), "+r"(lane_p));
+    const bool lane0 = lane_p == 0;
     // (routed through a shuffle: ptxas does not rematerialise a shuffle result from the constant bank)
     auto pin = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
-    const int nch = pin(p.nch), Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
+    const int nch = nch_p, Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
     const int scale_needed = pin(alpha_m1 ? 0 : 1);
     const uint32_t stepBr = (uint32_t)pin((int)stepB);
     sgn = pin(sgn);
@@ -440,8 +472,10 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
       if (tile >= ntlr) goto done;
       if (CW == kBsrCH || skip == 0) {
         B3_TR(warp, trit, 0);
+#if !SBP_B3_RECPOS
         const Rec r1 = load_rec(kBsrCH * pc + ps);
         advance();
+#endif
         const int nf = r0.a.y;
         const bool active = r0.a.z < Nr;  // padding records of the last chunk carry rows >= N and no fragments
         // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
@@ -488,8 +522,11 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         const bool work = active && nf > 0;
         // the operator fragments arrive ahead of the boxes: the first B operand and the ring addresses of the first two
         // fragments are fetched before the wait for the boxes
-        if (kB3Merged) mbar_wait(&bar_full[st], phase);
-        else mbar_wait(&fbar_full[fst], fphase);
+        // what-if 44 / 45 (no memory traffic): after the CTA's first tile a warp does not wait for any "full" barrier
+        const bool nowait = (SBP_B3_EXP == 44 || SBP_B3_EXP == 45) && tile != (int)blockIdx.x;
+        if (nowait) {
+        } else if (kB3Merged) mbar_wait_a(bar32 + 8u * (O_FULL + st), phase);
+        else mbar_wait_a(bar32 + 8u * (O_FFULL + fst), fphase);
         B3_TR(warp, trit, 1);
         double b0v = 0.0;
         uint32_t adr0 = su32, adr = su32;
@@ -498,7 +535,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             adr0 = conv(lds32<0>(sp));
             adr = conv(lds32<0>(min(sp + 4u * PS, spl)));  // address of fragment 1
         }
-        if (!kB3Merged) mbar_wait(&bar_full[st], phase);
+        if (!kB3Merged && !nowait) mbar_wait_a(bar32 + 8u * (O_FULL + st), phase);
         B3_TR(warp, trit, 2);
         if (PING) named_bar_sync(pp_me, 64);  // wait for the pipe token
         if (CW == 12 && p.sem) {  // block sem_n of this scheduler may multiply once sem_n - p.sem + 1... of its predecessors have finished
@@ -511,31 +548,47 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // ---- DMMA chain, two fragments per trip: operands one fragment ahead, ring codes two ahead ----
         if (work) {
             double a0[MT], a1[MT];
+            // staggered chains: two free-running warps of a scheduler overlap their chains at random, and while both are in
+            // their scalar phases the pipe idles; the gate keeps a warp from starting while its partner has just started
+            constexpr bool GATE = SBP_B3_GATE > 0 && CW == kBsrCH;
+            int got = 1;
+            if (GATE && lane0) got = atomicCAS(&gate[warp & 3], -1, warp) == -1;  // first try, issued ahead of the operand loads
             lds_tiles<MT, MTB>(a0, adr0);
+            if (GATE) {
+                if (lane0)
+                    while (!got) got = atomicCAS(&gate[warp & 3], -1, warp) == -1;
+                __syncwarp();
+            }
             B3_TR(warp, trit, 3);
             int rem = nf;
-            while (rem >= 2) {
-#if SBP_B3_EXP != 2
+            const int stop = GATE ? nf - (((nf * SBP_B3_GATE) >> 3) & ~1) : nf;  // fragments left when the gate opens again
+            auto trip = [&]() {
+#if SBP_B3_EXP != 2 && SBP_B3_EXP != 41 && SBP_B3_EXP != 42
                 lds_tiles<MT, MTB>(a1, adr);
 #else
                 a1[0] = __longlong_as_double(adr);
 #endif
                 const double b1v = flip(lds64<256>(sv));
-                adr = conv(lds32<0>(min(sp + 8u * PS, spl)));
+                adr = conv(kNoCodes ? (uint32_t)rem * 32u : lds32<0>(min(sp + 8u * PS, spl)));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a0[mt], b0v);
-#if SBP_B3_EXP != 2
+#if SBP_B3_EXP != 2 && SBP_B3_EXP != 41 && SBP_B3_EXP != 42
                 lds_tiles<MT, MTB>(a0, adr);
 #else
                 a0[0] = __longlong_as_double(adr);
 #endif
                 // fragment 2 of this trip = fragment 0 of the next one (unused past the end)
                 b0v = flip(lds64<512>(sv));
-                adr = conv(lds32<0>(min(sp + 12u * PS, spl)));
+                adr = conv(kNoCodes ? (uint32_t)rem * 32u + 160u : lds32<0>(min(sp + 12u * PS, spl)));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a1[mt], b1v);
                 sv += 512u, sp += 8u * PS, rem -= 2;
+            };
+            if (GATE) {
+                while (rem > stop) trip();
+                if (lane0) asm volatile("st.volatile.shared.s32 [%0], %1;\n" ::"r"(smem_u32(&gate[warp & 3])), "r"(-1) : "memory");
             }
+            while (rem >= 2) trip();
             if (rem) {
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a0[mt], b0v);
@@ -543,6 +596,11 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         }
 
         B3_TR(warp, trit, 4);
+#if SBP_B3_RECPOS
+        // the next block's record is requested now: its latency passes while the pipe drains and the results are staged
+        const Rec r1 = load_rec(kBsrCH * pc + ps);
+        advance();
+#endif
         const int nb = min(Bir - b0, TI);
         if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the other warp of this scheduler may start
         if (CW == 12 && p.sem) {
@@ -554,7 +612,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
         const bool scale_later = DEFER && scale_needed && !sat_block;
         if (XT) {  // the helper has put this block's quads of `extra` into the staging buffer (every item signals)
-            mbar_wait(&ext_full[warp], ext_phase);
+            mbar_wait_a(wbar32 + 8u * O_XFULL, ext_phase);
             ext_phase ^= 1;
         }
         if (active) {
@@ -646,9 +704,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&bar_empty[st]);    // the ring slots behind this item's window may be refilled
-            if (!kB3Merged) mbar_arrive(&fbar_empty[fst]);  // and so may the fragment buffers
+        if (lane0) {
+            mbar_arrive_a(bar32 + 8u * (O_EMPTY + st));    // the ring slots behind this item's window may be refilled
+            if (!kB3Merged) mbar_arrive_a(bar32 + 8u * (O_FEMPTY + fst));  // and so may the fragment buffers
         }
         B3_TR(warp, trit, 5);
 
@@ -660,7 +718,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             pv_state = (active ? 1 : 0) | (scale_later ? 2 : 0) | (hf ? 4 : 0);
         } else if (HELP) {
             // ---- results to the warp's staging buffer; a helper warp stores them (every item signals, active or not) ----
-            mbar_wait(&out_empty[warp], out_phase ^ 1);  // the helper has stored the previous contents (first item: passes)
+            if (SBP_B3_EXP != 45) mbar_wait_a(wbar32 + 8u * O_OEMPTY, out_phase ^ 1);  // the helper has stored the previous contents (first item: passes)
             B3_TR(warp, trit, 6);
             out_phase ^= 1;
             if (active) {
@@ -669,7 +727,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 if (!SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
             }
             __syncwarp();  // orders the lanes' stores before lane 0's arrive (release)
-            if (lane == 0) mbar_arrive(&out_full[warp]);
+            if (lane0) mbar_arrive_a(wbar32 + 8u * O_OFULL);
             B3_TR(warp, trit, 7);
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
@@ -707,18 +765,18 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         myslot = (myslot + CW) % kBsrCH;
       } else {
         // no block of this item: observe its boxes (later windows reach back into them) and release it at once
-        if (!kB3Merged) mbar_wait(&fbar_full[fst], fphase);
-        mbar_wait(&bar_full[st], phase);
-        if (lane == 0) {
-            mbar_arrive(&bar_empty[st]);
-            if (!kB3Merged) mbar_arrive(&fbar_empty[fst]);
+        if (!kB3Merged) mbar_wait_a(bar32 + 8u * (O_FFULL + fst), fphase);
+        mbar_wait_a(bar32 + 8u * (O_FULL + st), phase);
+        if (lane0) {
+            mbar_arrive_a(bar32 + 8u * (O_EMPTY + st));
+            if (!kB3Merged) mbar_arrive_a(bar32 + 8u * (O_FEMPTY + fst));
         }
         skip--;
       }
         // ---- next item ----
         if (++c == nch) {
             c = 0;
-            tile += gridDim.x;
+            tile += grid_p;
             b0 += tstepr;
             offB += stepBr;
             offB = min(offB, offB - ringBr);

@@ -83,6 +83,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // wait of a thread that has nothing else to do (TMA producers, store helpers): try_wait with a suspend-time hint, so that the
 // thread sleeps in hardware until the phase completes (or `ns` nanoseconds pass) instead of re-issuing a poll every few cycles
+// the same with a 32-bit shared address (kept in a register by the caller: `&static_shared_array[i]` costs S2R + LEA per use)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar32) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar32) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar32, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(bar32), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t ns = 20000) {
     uint32_t ok = 0;
     while (!ok)
