@@ -461,8 +461,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         __syncwarp();
         if (lane == 0) {
             const int yo = SBP_B3_EXP == 5 ? 0 : yb0;  // what-if 5: every tile writes the rows of tile 0 (L2-resident output)
-            if (rowA < Nr) tma_store_2d(&tmap_out, rowA, yo, so);
-            if (rowB < Nr) tma_store_2d(&tmap_out, rowB, yo, so + 8 * MT * 4);
+            if (rowA < Nr && !kNoStores) tma_store_2d(&tmap_out, rowA, yo, so);
+            if (rowB < Nr && !kNoStores) tma_store_2d(&tmap_out, rowB, yo, so + 8 * MT * 4);
             bulk_commit();
         }
     };
