@@ -54,6 +54,10 @@
 #define SBP_B3_GATE 0  // k > 0: staggered chains -- a consumer warp starts its chain only while the other warp of its scheduler is not
 #endif                 // inside the first k/8 of its own (shared-memory gate per scheduler); 0: free running.  Measured: k = 3..6 cost
                        // 8 % on config 3 (0.324-0.328 vs 0.299 ms in the same build), 6-13 % without any memory traffic
+#ifndef SBP_B3_PRO
+#define SBP_B3_PRO 0  // 1: a consumer warp steps to the next item and derives that item's addresses, masks and SAT data between
+#endif                // the DMMAs of its current chain's last trip (the integer work hides behind the tensor pipe), 0: at the item top
+                      // (measured: config 3 0.3175 vs 0.2913 ms, apply 0.2825 vs 0.2775; the same work placed after the chain: +3 %)
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -466,6 +470,57 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             bulk_commit();
         }
     };
+    // what a warp derives from the record of a row block before it can multiply (everything but the data itself)
+    struct Item {
+        int nf, rA, rB, lowbox, flags;  // fragments, first row of quad A / of quad B, the chunk's lowest box, 1D SAT flags
+        int r0w, mask, n0, n1, h0, h1;  // the lane's rows r0w, r0w + 1: SAT mask, node and half (instance pairs)
+        uint32_t baseB, sv, sp;         // ring window base (bytes), shared addresses of the block's fragments / ring codes
+        double2 sb;
+        double gs0, gs1;                // boundary data shared by all instances
+    };
+    auto prologue = [&](const Rec& r, uint32_t offB_, uint32_t svst_, uint32_t spst_) {
+        Item I;
+        I.nf = r.a.y, I.rA = r.a.z, I.rB = r.a.w, I.lowbox = r.b.y, I.flags = r.b.z;
+        // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
+        uint32_t baseB = (uint32_t)r.b.x * BOXB + offB_;
+        baseB = min(baseB, baseB - ringBr);
+        asm volatile("" : "+r"(baseB));
+        I.baseB = baseB;
+        I.sb = r.sb;
+        I.r0w = (t < 2 ? r.a.z : r.a.w - 4) + 2 * t;  // lane owns rows r0w, r0w + 1 (pair t of the block)
+        // b_j != 0 tested on the bit pattern (no trip through the FP64 pipe)
+        I.mask = (SAT == 1) ? ((((__double2hiint(r.sb.x) << 1) | __double2loint(r.sb.x)) != 0 ? 1 : 0) |
+                               (((__double2hiint(r.sb.y) << 1) | __double2loint(r.sb.y)) != 0 ? 2 : 0))
+                            : 0;
+        I.h0 = (paired && I.r0w >= Nh) ? 1 : 0, I.h1 = (paired && I.r0w + 1 >= Nh) ? 1 : 0;
+        I.n0 = I.r0w - I.h0 * Nh, I.n1 = I.r0w + 1 - I.h1 * Nh;
+        I.gs0 = 0.0, I.gs1 = 0.0;
+        if (SAT == 1 && I.mask && p.g_stride == 0) {
+            if (I.mask & 1) I.gs0 = __ldg(p.g + I.n0);
+            if (I.mask & 2) I.gs1 = __ldg(p.g + I.n1);
+        }
+        // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
+        I.sv = svst_ + (uint32_t)r.a.x * 256u, I.sp = spst_ + (uint32_t)r.a.x * (4u * PS);
+        return I;
+    };
+    constexpr bool PRO = SBP_B3_PRO && CW == kBsrCH && SBP_B3_RECPOS == 0;
+    // step to the next item: chunk / tile counters, ring offset, stage and phase of the barriers, fragment buffers
+    auto next_item = [&]() {
+        if (++c == nch) {
+            c = 0;
+            tile += grid_p;
+            b0 += tstepr;
+            offB += stepBr;
+            offB = min(offB, offB - ringBr);
+        }
+        svst += stvalB, spst += stposB;
+        if (++st == nstr) {
+            st = 0, phase ^= 1;
+            if (kB3Merged) svst = sval32, spst = spos32;
+        }
+        if (!kB3Merged && ++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
+    };
+    Item nxt = prologue(r0, offB, svst, spst);
     while (true) {
 #pragma unroll
      for (int hf = 0; hf < (DEFER ? 2 : 1); hf++) {
@@ -476,25 +531,15 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         const Rec r1 = load_rec(kBsrCH * pc + ps);
         advance();
 #endif
-        const int nf = r0.a.y;
-        const bool active = r0.a.z < Nr;  // padding records of the last chunk carry rows >= N and no fragments
-        // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
-        uint32_t baseB = (uint32_t)r0.b.x * BOXB + offB;
-        baseB = min(baseB, baseB - ringBr);
-        asm volatile("" : "+r"(baseB));
-        const double2 sb = r0.sb;
-        const int r0w = (t < 2 ? r0.a.z : r0.a.w - 4) + 2 * t;  // lane owns rows r0w, r0w + 1 (pair t of the block)
-        // b_j != 0 tested on the bit pattern (no trip through the FP64 pipe)
-        const int mask = (SAT == 1) ? ((((__double2hiint(sb.x) << 1) | __double2loint(sb.x)) != 0 ? 1 : 0) |
-                                       (((__double2hiint(sb.y) << 1) | __double2loint(sb.y)) != 0 ? 2 : 0))
-                                    : 0;
-        const int h0 = (paired && r0w >= Nh) ? 1 : 0, h1 = (paired && r0w + 1 >= Nh) ? 1 : 0;
-        const int n0 = r0w - h0 * Nh, n1 = r0w + 1 - h1 * Nh;
-        double gs0 = 0.0, gs1 = 0.0;
-        if (SAT == 1 && mask && p.g_stride == 0) {
-            if (mask & 1) gs0 = __ldg(p.g + n0);
-            if (mask & 2) gs1 = __ldg(p.g + n1);
-        }
+        const Item I = PRO ? nxt : prologue(r0, offB, svst, spst);
+        const int nf = I.nf, r0w = I.r0w, mask = I.mask, n0 = I.n0, n1 = I.n1, h0 = I.h0, h1 = I.h1;
+        const bool active = I.rA < Nr;  // padding records of the last chunk carry rows >= N and no fragments
+        const uint32_t baseB = I.baseB;
+        const double2 sb = I.sb;
+        double gs0 = I.gs0, gs1 = I.gs1;
+        // this item's first tensor row, barrier stages and phases (PRO steps on before they are used for the last time)
+        const int b0c = b0, stc = st, fstc = fst;
+        bool stepped = false;
         double(&acc)[MT][2] = accs[DEFER ? hf : 0];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
@@ -510,7 +555,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
         // this row block's fragments in the stage buffers: B operand of this lane, ring code of this lane's column
-        uint32_t sv = svst + (uint32_t)r0.a.x * 256u, sp = spst + (uint32_t)r0.a.x * (4u * PS);
+        uint32_t sv = I.sv, sp = I.sp;
         const uint32_t spl = sp + (uint32_t)(nf - 1) * (4u * PS);  // last code of the block (look-ahead loads are clamped to it)
 
         // byte code -> shared address of the lane's A operand (m-tile 0): add the window base, wrap, add the lane's row
@@ -572,6 +617,11 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 adr = conv(kNoCodes ? (uint32_t)rem * 32u : lds32<0>(min(sp + 8u * PS, spl)));
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) B3_DMMA(acc[mt][0], acc[mt][1], a0[mt], b0v);
+                if (PRO && rem <= 3) {  // last trip: the pipe holds seven DMMAs of this warp -- the next item's integer work goes here
+                    next_item();
+                    nxt = prologue(r1, offB, svst, spst);
+                    stepped = true;
+                }
 #if SBP_B3_EXP != 2 && SBP_B3_EXP != 41 && SBP_B3_EXP != 42
                 lds_tiles<MT, MTB>(a0, adr);
 #else
@@ -595,13 +645,17 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             }
         }
 
+        if (PRO && !stepped) {  // blocks with fewer than two fragments, padding records
+            next_item();
+            nxt = prologue(r1, offB, svst, spst);
+        }
         B3_TR(warp, trit, 4);
 #if SBP_B3_RECPOS
         // the next block's record is requested now: its latency passes while the pipe drains and the results are staged
         const Rec r1 = load_rec(kBsrCH * pc + ps);
         advance();
 #endif
-        const int nb = min(Bir - b0, TI);
+        const int nb = min(Bir - b0c, TI);
         if (PING) named_bar_arrive(pp_next, 64);  // chain issued: the other warp of this scheduler may start
         if (CW == 12 && p.sem) {
             if (lane == 0) atomicAdd(&sem_fin[warp & 3], 1);
@@ -609,7 +663,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         }
         // blocks that carry SAT terms finish their accumulators now (the terms read the ring); for the others a deferred
         // epilogue also takes over the scaling by alpha
-        const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && r0.b.z != 0);
+        const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && I.flags != 0);
         const bool scale_later = DEFER && scale_needed && !sat_block;
         if (XT) {  // the helper has put this block's quads of `extra` into the staging buffer (every item signals)
             mbar_wait_a(wbar32 + 8u * O_XFULL, ext_phase);
@@ -623,7 +677,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             // element offset of node r of the lane's tensor row (m-tile 0) inside the ring: r lies in the chunk's window
             auto ring_elem = [&](int r) {
                 const int q = r / BX;
-                uint32_t o = baseB + (uint32_t)(q - r0.b.y) * BOXB + (uint32_t)(r - q * BX) * 8u;
+                uint32_t o = baseB + (uint32_t)(q - I.lowbox) * BOXB + (uint32_t)(r - q * BX) * 8u;
                 return min(o, o - ringB);
             };
             if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
@@ -632,7 +686,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 for (int mt = 0; mt < MT; mt++) {
                     if (p.g_stride != 0) {  // per-instance boundary data
                         const int il = 8 * mt + g;
-                        const long long row = b0 + (il < nb ? il : 0);
+                        const long long row = b0c + (il < nb ? il : 0);
                         if (mask & 1) gs0 = __ldg(p.g + (paired ? 2 * row + h0 : row) * p.g_stride + n0);
                         if (mask & 2) gs1 = __ldg(p.g + (paired ? 2 * row + h1 : row) * p.g_stride + n1);
                     }
@@ -640,15 +694,15 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (mask & 2) acc[mt][1] += sb.y * (*reinterpret_cast<const double*>(su_lane + o1 + mt * MTB) - gs1);
                 }
             }
-            if (SAT == 2 && r0.b.z != 0) {
+            if (SAT == 2 && I.flags != 0) {
                 // 1D SATs at nodes 0 and Nh-1 of every instance (the record flags the block rows that carry one): lane l
                 // evaluates the term for the warp's tensor rows l (and l + 32), the owning lane fetches it by shuffle
-                const int flags = r0.b.z;
+                const int flags = I.flags;
 #pragma unroll 1
                 for (int k = 0; k < 8; k++) {
                     const bool left = (flags >> k) & 1, right = (flags >> (8 + k)) & 1;
                     if (!(left | right)) continue;
-                    const int r = (k < 4 ? r0.a.z : r0.a.w - 4) + k;
+                    const int r = (k < 4 ? I.rA : I.rB - 4) + k;
                     const int h = (paired && r >= Nh) ? 1 : 0;
                     // ring_elem is relative to the lane's own tensor row g; here lane l reads tensor row il
                     const uint32_t o = ring_elem(r);
@@ -658,7 +712,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         const int il = lane + 32 * kk;  // tensor row within the tile
                         sv2[kk] = 0.0;
                         if (il < 8 * MT && il < nb) {
-                            const long long row = (long long)b0 + il, inst = paired ? 2 * row + h : row;
+                            const long long row = (long long)b0c + il, inst = paired ? 2 * row + h : row;
                             const double u = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_u) + o +
                                                                               (size_t)il * (BX * 8));
                             double lb = sat_lb, rbv = sat_rb;
@@ -705,8 +759,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         }
         __syncwarp();
         if (lane0) {
-            mbar_arrive_a(bar32 + 8u * (O_EMPTY + st));    // the ring slots behind this item's window may be refilled
-            if (!kB3Merged) mbar_arrive_a(bar32 + 8u * (O_FEMPTY + fst));  // and so may the fragment buffers
+            mbar_arrive_a(bar32 + 8u * (O_EMPTY + stc));    // the ring slots behind this item's window may be refilled
+            if (!kB3Merged) mbar_arrive_a(bar32 + 8u * (O_FEMPTY + fstc));  // and so may the fragment buffers
         }
         B3_TR(warp, trit, 5);
 
@@ -714,7 +768,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             if (acc[0][0] == 1.2345e300) p.dU[0] = acc[MT - 1][1];
         } else if (DEFER) {
             if (pv_state & 1) emit(accs[DEFER ? hf ^ 1 : 0], pv_rowA, pv_rowB, pv_b0, (pv_state & 2) != 0);
-            pv_rowA = r0.a.z, pv_rowB = r0.a.w, pv_b0 = b0;
+            pv_rowA = I.rA, pv_rowB = I.rB, pv_b0 = b0c;
             pv_state = (active ? 1 : 0) | (scale_later ? 2 : 0) | (hf ? 4 : 0);
         } else if (HELP) {
             // ---- results to the warp's staging buffer; a helper warp stores them (every item signals, active or not) ----
@@ -732,14 +786,14 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         } else if (OUT == 2) {
             // ---- results through TMA: lane (g,t) deposits rows r0w, r0w+1 of instance 8mt + g in the warp's staging buffer;
             //      one lane stores quad A and quad B as {4 rows x 8*MT instances} boxes ----
-            if (active) emit(acc, r0.a.z, r0.a.w, b0, false);
+            if (active) emit(acc, I.rA, I.rB, b0c, false);
         } else if (active && r0w < N) {
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
                 const int il = 8 * mt + g;
                 if (il >= nb) continue;
                 double y0 = acc[mt][0], y1 = acc[mt][1];
-                double* yp = p.dU + (long long)(b0 + il) * N + r0w;
+                double* yp = p.dU + (long long)(b0c + il) * N + r0w;
                 if (VEC) {  // N even: row r0w + 1 exists
                     if (p.beta != 0.0) {
                         const double2 o = *reinterpret_cast<const double2*>(yp);
@@ -773,20 +827,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         }
         skip--;
       }
-        // ---- next item ----
-        if (++c == nch) {
-            c = 0;
-            tile += grid_p;
-            b0 += tstepr;
-            offB += stepBr;
-            offB = min(offB, offB - ringBr);
-        }
-        svst += stvalB, spst += stposB;
-        if (++st == nstr) {
-            st = 0, phase ^= 1;
-            if (kB3Merged) svst = sval32, spst = spos32;
-        }
-        if (!kB3Merged && ++fst == kB3FragStages) fst = 0, fphase ^= 1, svst = sval32, spst = spos32;
+        if (!PRO) next_item();
      }
     }
 done:
