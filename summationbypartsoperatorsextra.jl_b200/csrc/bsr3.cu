@@ -58,6 +58,9 @@
 #define SBP_B3_PRO 0  // 1: a consumer warp steps to the next item and derives that item's addresses, masks and SAT data between
 #endif                // the DMMAs of its current chain's last trip (the integer work hides behind the tensor pipe), 0: at the item top
                       // (measured: config 3 0.3175 vs 0.2913 ms, apply 0.2825 vs 0.2775; the same work placed after the chain: +3 %)
+#ifndef SBP_B3_MERGE8
+#define SBP_B3_MERGE8 1  // 1: a block whose quads are adjacent in memory (rows r .. r+7: banded operators) leaves as ONE {8 x instances}
+#endif                   // TMA box (64-byte rows, staging stores free of bank conflicts) instead of two {4 x instances} boxes
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -137,7 +140,10 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
 __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
-           const __grid_constant__ CUtensorMap tmap_ex) {
+           const __grid_constant__ CUtensorMap tmap_ex, const __grid_constant__ CUtensorMap tmap_out8) {
+    // MERGE8: adjacent quads of a block are staged as [instance][8 rows] and stored by one box (not when the staging buffer also
+    // carries the extra operand of a fused stage update, which arrives quad by quad)
+    constexpr bool MERGE8 = SBP_B3_MERGE8 && HELP && SBP_B3_EXP == 0;
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
     constexpr int TI = 8 * MT;
@@ -262,8 +268,12 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
                         const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
                         if (rowA[k] < N && !kNoStores) {
-                            tma_store_2d(&tmap_out, rowA[k], b0, so);
-                            if (rowB[k] < N) tma_store_2d(&tmap_out, rowB[k], b0, so + 8 * MT * 4);
+                            if (MERGE8 && !XT && rowB[k] == rowA[k] + 4) {
+                                tma_store_2d(&tmap_out8, rowA[k], b0, so);
+                            } else {
+                                tma_store_2d(&tmap_out, rowA[k], b0, so);
+                                if (rowB[k] < N) tma_store_2d(&tmap_out, rowB[k], b0, so + 8 * MT * 4);
+                            }
                             bulk_commit();
                             bulk_wait_read<0>();
                         }
@@ -371,6 +381,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     const char* const su_lane = reinterpret_cast<const char*>(s_u + g * BX);  // tensor row 8 mt + g lives MTB * mt further
     double* const so = s_out + (size_t)warp * (2 * 8 * MT * 4);
     double* const sq = so + (t >> 1) * (8 * MT * 4) + g * 4 + (t & 1) * 2;
+    double* const sq8 = so + g * 8 + 2 * t;  // MERGE8 layout
 
     // item records (one per row block, independent of the tile): fetched two items ahead
     struct Rec {
@@ -776,8 +787,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             B3_TR(warp, trit, 6);
             out_phase ^= 1;
             if (active) {
+                if (MERGE8 && !XT && I.rB == I.rA + 4) {  // [instance][8 rows]: lane (g, t) owns rows 2t, 2t + 1 of instance 8 mt + g
 #pragma unroll
-                for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
+                    for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq8 + mt * 64) = make_double2(acc[mt][0], acc[mt][1]);
+                } else {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq + mt * 32) = make_double2(acc[mt][0], acc[mt][1]);
+                }
                 if (!SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> visible to the TMA (async proxy)
             }
             __syncwarp();  // orders the lanes' stores before lane 0's arrive (release)
@@ -859,6 +875,9 @@ static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     if (rc) return rc;
     rc = OUT == 2 ? make_tmap(&tmap_out, p.dU, p.N, p.B, 4, TI) : (tmap_out = tmap, SBP_OK);
     if (rc) return rc;
+    CUtensorMap tmap_out8 = tmap_out;  // adjacent quads of a block as one box of 8 rows
+    if (SBP_B3_MERGE8 && HELP && OUT == 2) rc = make_tmap(&tmap_out8, p.dU, p.N, p.B, 8, TI);
+    if (rc) return rc;
     CUtensorMap tmap_ex = tmap_out;  // fused stage update with an extra operand: its quads travel like the output's
     if (FUSED && HELP && p.extra && p.cb != 0.0) rc = make_tmap(&tmap_ex, p.extra, p.N, p.B, 4, TI);
     if (SBP_B3_EXP == 11 || SBP_B3_EXP == 12) rc = make_tmap(&tmap_ex, p.dU, p.N, p.B, SBP_B3_EXP == 11 ? 32 : 16, TI);
@@ -866,7 +885,7 @@ static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
     SBP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (p.B + TI - 1) / TI;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count));
-    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out, tmap_ex);
+    kern<<<grid, THREADS, smem, ctx->stream>>>(p, tmap, tmap_out, tmap_ex, tmap_out8);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
