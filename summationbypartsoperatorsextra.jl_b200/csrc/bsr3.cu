@@ -438,6 +438,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     auto pin = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
     const int nch = nch_p, Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
     const int scale_needed = pin(alpha_m1 ? 0 : 1);
+    // comparisons of double parameters, made once: a DSETP inside the item loop queues behind the DMMAs of the other warp (ncu: 4 %
+    // of the fused kernel's samples on five of them per block)
+    const int cbnz = pin(p.cb != 0.0 ? 1 : 0);
+    const bool XTc = HELP && FUSED && cbnz;  // = XT
+    // (measured and dropped: -b_j g_j as the accumulators' initial value, one DFMA per SAT entry after the chain instead of DADD +
+    // DFMA: config 3 0.3095 vs 0.2929 ms; two instead of three FP64 instructions per entry in stage updates without an extra
+    // operand: SSPRK53 step 1.658 vs 1.622 ms)
     const uint32_t stepBr = (uint32_t)pin((int)stepB);
     sgn = pin(sgn);
     uint32_t svst = sval32, spst = spos32;  // fragment buffers of stage st
@@ -556,7 +563,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
         // stage update: the lane's entries of `extra` are requested now and consumed after the chain
         double2 ex[(FUSED && !HELP) ? MT : 1];  // (with helper warps the operand comes through the staging buffer: XT)
-        const bool with_extra = FUSED && p.cb != 0.0 && active && r0w < Nr;
+        const bool with_extra = FUSED && cbnz && active && r0w < Nr;
         if (FUSED && !HELP && with_extra) {
             const int nbx = min(Bir - b0, TI);
 #pragma unroll
@@ -676,7 +683,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // epilogue also takes over the scaling by alpha
         const bool sat_block = (SAT == 1 && mask != 0) || (SAT == 2 && I.flags != 0);
         const bool scale_later = DEFER && scale_needed && !sat_block;
-        if (XT) {  // the helper has put this block's quads of `extra` into the staging buffer (every item signals)
+        if (XTc) {  // the helper has put this block's quads of `extra` into the staging buffer (every item signals)
             mbar_wait_a(wbar32 + 8u * O_XFULL, ext_phase);
             ext_phase ^= 1;
         }
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     double2 e = make_double2(0.0, 0.0);
-                    if (with_extra) e = XT ? *reinterpret_cast<const double2*>(sq + mt * 32) : ex[(FUSED && !HELP) ? mt : 0];
+                    if (with_extra) e = XTc ? *reinterpret_cast<const double2*>(sq + mt * 32) : ex[(FUSED && !HELP) ? mt : 0];
                     const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
                     const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
                     acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
@@ -787,7 +794,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             B3_TR(warp, trit, 6);
             out_phase ^= 1;
             if (active) {
-                if (MERGE8 && !XT && I.rB == I.rA + 4) {  // [instance][8 rows]: lane (g, t) owns rows 2t, 2t + 1 of instance 8 mt + g
+                if (MERGE8 && !XTc && I.rB == I.rA + 4) {  // [instance][8 rows]: lane (g, t) owns rows 2t, 2t + 1 of instance 8 mt + g
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq8 + mt * 64) = make_double2(acc[mt][0], acc[mt][1]);
                 } else {
