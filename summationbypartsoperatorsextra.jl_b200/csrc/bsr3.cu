@@ -61,6 +61,10 @@
 #ifndef SBP_B3_MERGE8
 #define SBP_B3_MERGE8 1  // 1: a block whose quads are adjacent in memory (rows r .. r+7: banded operators) leaves as ONE {8 x instances}
 #endif                   // TMA box (64-byte rows, staging stores free of bank conflicts) instead of two {4 x instances} boxes
+#ifndef SBP_B3_GREEDY
+#define SBP_B3_GREEDY 1  // 1: the box producer keeps the ring full -- with every item it requests all boxes of its stream (this tile and
+#endif                   // the following ones) that fit behind the windows of the unreleased items, instead of just the boxes the item
+                         // needs: the first window of the next tile arrives while the last chunks of this one are multiplied
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -307,6 +311,12 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             const uint32_t s_u32 = smem_u32(s_u), s_val32 = smem_u32(s_val), s_pos32 = smem_u32(s_pos);
             const uint32_t full32 = smem_u32(pfull);
             int4 cm = __ldg(p.chmeta);
+            // GREEDY: next box of this CTA's stream (tile rtile, box rj), boxes requested counted from the current tile's box 0,
+            // boxes left in the stream, and the window bases of the last items (relative to the current tile)
+            long long rtile = blockIdx.x, req = 0;
+            long long stream_left = (long long)blockIdx.x < ntiles ? ((ntiles - 1 - blockIdx.x) / gridDim.x + 1) * p.nbt : 0;
+            int rj = 0;
+            int lo_hist[kB3Stages] = {};
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
                 int jb = 0, x = 0;  // boxes of this tile already requested, node coordinate of the next box
@@ -315,7 +325,35 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (round > 0) B3_PARK(&pempty[st], (round - 1) & 1);
                     B3_TR(warp, trp, 0);
                     const uint32_t bar = full32 + 8u * st;
-                    if (boxes) {
+                    if (boxes && SBP_B3_GREEDY && !kNoLoads) {
+                        // lowest box (relative to this tile) that an unreleased item may still read: item s - D, D = nst - 1
+                        for (int k = kB3Stages - 1; k > 0; k--) lo_hist[k] = lo_hist[k - 1];
+                        lo_hist[0] = cm.z;
+                        const long long fit = (long long)lo_hist[nst - 1] + nbox - req;  // free ring slots
+                        const int n = (int)max(0LL, min(fit, stream_left));
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((unsigned)n * BOXB)
+                                     : "memory");
+                        for (int k = 0; k < n; k++) {
+                            if (p.pf > 0) {
+                                int jp = rj + p.pf;
+                                long long tp = rtile;
+                                if (jp >= p.nbt) jp -= p.nbt, tp += gridDim.x;
+                                if (tp < ntiles)
+                                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(&tmap),
+                                                 "r"(jp * BX), "r"((int)(tp * TI))
+                                                 : "memory");
+                            }
+                            const uint32_t dst = s_u32 + (uint32_t)slot * BOXB;
+                            asm volatile(
+                                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
+                                "{%2, %3}], [%4];\n" ::"r"(dst),
+                                "l"(&tmap), "r"(rj * BX), "r"((int)(rtile * TI)), "r"(bar)
+                                : "memory");
+                            if (++slot == nbox) slot = 0;
+                            if (++rj == p.nbt) rj = 0, rtile += gridDim.x;
+                        }
+                        req += n, stream_left -= n;
+                    } else if (boxes) {
                         const int jn = cm.w;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar),
                                      "r"(kNoLoads ? 0u : (unsigned)(jn - jb) * BOXB)
@@ -365,9 +403,14 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (++st == pst) st = 0, round++;
                     cm = cmn;
                 }
-                // boxes of the tile that no chunk needs are skipped: keep slot == (virtual box index) mod nbox
-                slot += (p.nbt - jb) % nbox;
-                if (slot >= nbox) slot -= nbox;
+                if (boxes && SBP_B3_GREEDY && !kNoLoads) {  // the next tile's box 0 becomes the origin
+                    req -= p.nbt;
+                    for (int k = 0; k < kB3Stages; k++) lo_hist[k] -= p.nbt;
+                } else {
+                    // boxes of the tile that no chunk needs are skipped: keep slot == (virtual box index) mod nbox
+                    slot += (p.nbt - jb) % nbox;
+                    if (slot >= nbox) slot -= nbox;
+                }
             }
         }
         return;
