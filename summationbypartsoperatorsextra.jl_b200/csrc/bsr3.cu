@@ -982,7 +982,7 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     // helpers fetch its quads by TMA as soon as the previous block's results have been read out)
     // (measured: 2D RHS N = 1296 0.362 ms per stage with the extra operand against 0.414 on k_bsr; 1D RHS N = 101 0.279 against
     // 0.240 -> those stay on k_bsr)
-    if (p.fused && (cw != 9 || satmode == 0 || (satmode == 2 && p.cb != 0.0))) return false;
+    if (p.fused && (cw != 9 || satmode == 0 || (satmode == 2 && p.cb != 0.0 && enabled != 2))) return false;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;
