@@ -11,21 +11,23 @@
 //    (sbp_op::d_bsr_pos3): per fragment one add, one unsigned min (wrap) and one add instead of shift/mask/compare/
 //    select/multiply-add; the chain is unrolled by two fragments over two explicit A-operand register sets, operands are
 //    fetched by ld.shared at 32-bit addresses with compile-time m-tile offsets, one fragment ahead;
-//  * loop invariants that the compiler rematerialised at every use are pinned in registers, the warp index is made
-//    provably uniform (TMA stores without the per-lane vote loops), item records are fetched two items ahead;
-//  * box stages and operator-fragment stages are decoupled (p.nst box stages, two fragment stages): with plain 16-byte
-//    stores (no staging buffers) the ring of config 3 holds two chunks of lookahead at 56 instances per tile;
-//  * -DSBP_B3_EXP=n what-if builds and SBP_BSR_SKEW (start-up delay of every second consumer warp).
+//  * loop invariants that the compiler rematerialised at every use are pinned in registers (also barrier addresses, lane,
+//    record pointer, comparisons of double parameters), the warp index is made provably uniform (TMA stores without the
+//    per-lane vote loops), item records are fetched one item ahead;
+//  * box stages and operator-fragment stages are decoupled (p.nst box stages, two fragment stages);
 //  * four store-helper warps (HELP) take the staging buffers from the consumer warps through mbarriers and issue the TMA
 //    stores: the consumer warps neither issue stores nor wait for their buffers (config 3: 0.3256 -> 0.311 ms);
-// Result (profiles/r1k_bsr3_notes.txt): 14 % fewer warp instructions, 15 % less time outside the DMMA chain -- and, before
-// the helper warps, the same 0.326-0.330 ms on BASELINE config 3 as k_bsr.  The what-if builds show why: without
-// DMMAs 0.252 ms, without output 0.166 ms (= the tensor pipe: 2 warps x 64 DMMA x 16 cycles per scheduler and chunk),
-// full kernel 0.330 ms = pipe time + the non-chain time of a warp: the two consumer warps of a scheduler run their
-// chains at the same time and their scalar phases at the same time, whatever the pipeline depth, the start-up skew or
-// the length of the scalar phase (time saved there reappears as waiting on the stage barrier).  An intermediate version
-// that fetched the operator fragments from the L2-resident image straight into registers (no fragment stages at all)
-// was 30 % SLOWER: the L2 round trip under load is exposed once per item.
+//  * round 2: L2 prefetch of the box stream (cp.async.bulk.prefetch.tensor.2d.L2), proxy fence on the helper side, a box
+//    producer that keeps the ring full across tile changes (GREEDY), blocks with adjacent quads staged as [instance][8 rows]
+//    and stored by one {8 x instances} box (MERGE8): config 3 0.291 ms, config 1 batched 0.155 ms;
+//  * -DSBP_B3_EXP=n what-if builds, -DSBP_B3_TRACE=1 clock64 timeline, SBP_BSR_SKEW.
+// What bounds it (profiles/r2_bsr_notes.txt): the consumer loop -- without any memory traffic it needs
+// 0.256 ms on config 3 (1944 cycles of DMMA issue per item and scheduler, 2700-2950 cycles measured: two free-running warps
+// per scheduler, ~1000 cycles of serial non-chain work per block); all memory traffic together adds 0.035 ms.  The round-1
+// reading "without output 0.166 ms = the tensor pipe" came from a what-if build in which ptxas had deleted most DMMAs (their
+// accumulators were never read) and is withdrawn.  An intermediate version that fetched the operator fragments from the
+// L2-resident image straight into registers (no fragment stages at all) was 30 % SLOWER: the L2 round trip under load is
+// exposed once per item.
 #include <algorithm>
 #include "bsr.cuh"
 
