@@ -818,6 +818,34 @@ def test_block_sparse_kernels_are_deterministic(ctx, organisation):
         assert rel_err(first[b], semio.rhs(U[b], 0.3)) <= TOL
 
 
+@pytest.mark.parametrize("N", [101, 104])
+def test_block_sparse_banded_1d_is_deterministic(ctx, N):
+    """Same race detector for the banded 1D route (odd N as instance pairs / even N): every block leaves as ONE {8 x instances}
+    box, a tile has only 2-4 items, so the box producer's requests run several tiles ahead of the consumers."""
+    D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    D.storage = "sparse"
+    Do = O.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
+    lbc, rbc = (lambda t: 0.3 + t), (lambda t: -0.2)
+    semi = S.VariableLinearAdvectionNonperiodicSemidiscretization(D, None, lambda x: 1.0, False, lbc, rbc)
+    semio = O.AdvectionSemi1D(Do, lambda x: 1.0, lbc, rbc)
+    B = 148 * 64 * 2 * 3 + 38  # three tiles of instance pairs per SM + a ragged tail
+    u, du = ctx.upload(rand_batch(B, N, 51)), S.DeviceBatch.empty(ctx, B, N)
+    out = S.DeviceBatch.empty(ctx, B, N)
+    semi(du, u, None, 0.2)
+    first = du.to_host()
+    semi.stage(out, u, 0.2, 1.0, 2e-3)
+    first_stage = out.to_host()
+    for rep in range(100):
+        semi(du, u, None, 0.2)
+        semi.stage(out, u, 0.2, 1.0, 2e-3)
+        if rep % 10 == 9:
+            assert np.array_equal(du.to_host(), first) and np.array_equal(out.to_host(), first_stage), rep
+    U = u.to_host()
+    for b in (0, 1, B // 2, B - 2, B - 1):
+        r = semio.rhs(U[b], 0.2)
+        assert rel_err(first[b], r) <= TOL and rel_err(first_stage[b], U[b] + 2e-3 * r) <= TOL
+
+
 # ---- f4: batched construction objective ------------------------------------------------------------------------------
 @pytest.mark.parametrize("structure", [dict(), dict(bandwidth=2, size_boundary=4), dict(bandwidth=3, size_boundary=6, different_values=False),
                                        "sparsity"])
