@@ -431,7 +431,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     const int nrb = (int)rows.size() / 2, nch = (nrb + CH - 1) / CH;
     auto block_row = [&](int rb, int g) { return (g < 4 ? rows[2 * rb] : rows[2 * rb + 1] - 4) + g; };
     constexpr int PS = 4;  // ring codes per fragment
-    std::vector<int> rbf(nrb + 1, 0), pos;
+    std::vector<int> rbf(nrb + 1, 0), pos, diag(8 * (size_t)nrb, -1);
     std::vector<double> frag;
     std::vector<int> cmin(nch, N), cmax(nch, 0);
     for (int rb = 0; rb < nrb; rb++) {
@@ -441,6 +441,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
             const int r = block_row(rb, g);
             if (r >= N) continue;
             for (int j = rowptr[r]; j < rowptr[r + 1]; j++) u.push_back(col[j]);
+            u.push_back(r);  // the diagonal entry always has a place in the image (SAT and stage-update terms are folded into it)
             // the block's own rows are part of the chunk's window (the SAT epilogues read u_j from the ring)
             cmin[c] = std::min(cmin[c], r);
             cmax[c] = std::max(cmax[c], r + 1);
@@ -484,6 +485,8 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
                 const int w = where[k];
                 frag[(f0 + w / 4) * 32 + (size_t)g * 4 + (w & 3)] += val[j];  // lane = 4*g + t; duplicates accumulate
             }
+            const int w = where[(int)(std::lower_bound(u.begin(), u.end(), r) - u.begin())];
+            diag[8 * (size_t)rb + g] = (int)((f0 + w / 4) * 32 + (size_t)g * 4 + (w & 3));
         }
         rbf[rb + 1] = (int)(f0 + nf);
         if (!u.empty()) {
@@ -583,6 +586,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     op->bsr_maxf = maxf;
     op->bsr_nrb = nrb;
     op->bsr_rows = rows;
+    op->bsr_diag = diag;
     op->bsr_frags = (int64_t)frag.size() / 32;
     if (frag.empty()) {
         frag.assign(32, 0.0);
@@ -896,7 +900,8 @@ int32_t sbp_op_destroy(sbp_op* op) {
                     op->d_col,       op->d_val,      op->d_slice_ptr, op->d_sell_col, op->d_sell_val, op->d_b,
                     op->d_mode,      op->d_bnd_node, op->d_bnd_tau,  op->d_a,        op->d_q_consts, op->d_wsym,
                     op->d_frag4,     op->d_wfrag4,   op->d_bsr_val,  op->d_bsr_pos,  op->d_bsr_rbmeta, op->d_bsr_chmeta,
-                    op->d_rb_bdiag,  op->d_bsr_item, op->d_bsr_pos3, op->d_csr_rowptr, op->d_csr_col, op->d_csr_val};
+                    op->d_rb_bdiag,  op->d_bsr_item, op->d_bsr_pos3, op->d_csr_rowptr, op->d_csr_col, op->d_csr_val,
+                    op->d_bsr_val_sat, op->d_bsr_val_stage, op->d_bsr_diagmask};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete op;
@@ -1031,6 +1036,27 @@ int32_t sbp_op_advection2d_create(sbp_ctx* ctx, const sbp_op* A, const double* h
                 if (i < A->bsr_N && h_mode[i % N] == 1) rbb[8 * (size_t)rb + r] = h_b[i % N];  // bsr_N = 2N: instance pairs
             }
         rc = upload(&op->d_rb_bdiag, rbb);
+        // fragments of A - diag(b): the SAT's u-term rides on the tensor pipe (bsr3.cu, satfold)
+        if (!rc && A->bsr_frags > 0 && A->bsr_diag.size() == 8 * (size_t)A->bsr_nrb) {
+            const size_t nv = (size_t)A->bsr_frags * 32;
+            std::vector<double> img(nv);
+            std::vector<unsigned char> mask(nv, 0);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+                cudaMemcpy(img.data(), A->d_bsr_val, nv * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                set_error("advection2d_create: device copy failed");
+                rc = SBP_ECUDA;
+            }
+            for (int rb = 0; rb < A->bsr_nrb && !rc; rb++)
+                for (int r = 0; r < 8; r++) {
+                    const int k = A->bsr_diag[8 * (size_t)rb + r];
+                    if (k < 0) continue;
+                    mask[k] = 1;
+                    img[k] -= rbb[8 * (size_t)rb + r] / A->scale;  // launch_bsr multiplies the image by alpha * scale
+                }
+            if (!rc) rc = upload(&op->d_bsr_val_sat, img);
+            if (!rc) rc = upload(&op->d_bsr_diagmask, mask);
+            if (!rc && cudaMalloc(&op->d_bsr_val_stage, nv * 8) != cudaSuccess) rc = SBP_ENOMEM;
+        }
     }
     if (!rc) rc = upload(&op->d_q_consts, qc);
     if (!rc) {

@@ -636,6 +636,10 @@ int32_t launch_bsr(sbp_ctx* ctx, const sbp_op* op, double* dU, const double* U, 
     p.alpha = alpha * op->scale;
     p.beta = beta;
     p.rb_bdiag = adv ? adv->d_rb_bdiag : nullptr;
+    if (adv && adv->d_bsr_val_sat && adv->inner == op) {  // (launch_bsr3 decides whether the folded image is used)
+        p.val_sat = adv->d_bsr_val_sat, p.val_stage = adv->d_bsr_val_stage, p.diagmask = adv->d_bsr_diagmask;
+        p.nvals = (long long)op->bsr_frags * 32;
+    }
     p.g = g;
     p.g_stride = g_stride;
     if (sat) p.sat = *sat;

@@ -26,6 +26,13 @@ struct BsrParams {
     int fused = 0;
     int skew = 0;                     // bsr3.cu: start-up delay (cycles) of the second consumer warp of every scheduler
     int pf = 0;                       // bsr3.cu: L2 prefetch distance of the box producer, in boxes of its stream (0: none)
+    // SAT u-term folded into the operator (k_bsr3 with 2D SATs): val_sat = fragments of A - diag(b); stage updates run on
+    // val_stage = ch * val_sat - ca * (diagonal mask), written by a small kernel in front of the launch
+    const double* val_sat = nullptr;
+    double* val_stage = nullptr;
+    const unsigned char* diagmask = nullptr;
+    long long nvals = 0;
+    int satfold = 0;                  // 1: the image in `val` contains the fold (set by launch_bsr3)
     int sem = 0;                      // bsr3.cu, 12 consumer warps: at most `sem` of the three warps of a scheduler multiply at a time (0: off)
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
     const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows

@@ -67,6 +67,10 @@
 #define SBP_B3_GREEDY 1  // 1: the box producer keeps the ring full -- with every item it requests all boxes of its stream (this tile and
 #endif                   // the following ones) that fit behind the windows of the unreleased items, instead of just the boxes the item
                          // needs: the first window of the next tile arrives while the last chunks of this one are multiplied
+#ifndef SBP_B3_SATFOLD
+#define SBP_B3_SATFOLD 1  // 1: 2D RHS / stage launches of the helper kernel run on the image of A - diag(b) (stage updates: ch (A - B) - ca I,
+#endif                    // rebuilt by k_stage_image per launch): no ring loads and one FP64 instruction less per SAT entry, no
+                          // ca * u term and no scaling by ch after the chain
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -486,6 +490,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // comparisons of double parameters, made once: a DSETP inside the item loop queues behind the DMMAs of the other warp (ncu: 4 %
     // of the fused kernel's samples on five of them per block)
     const int cbnz = pin(p.cb != 0.0 ? 1 : 0);
+    // the launcher gives SAT == 1 helper kernels the folded image (or does not take this kernel at all)
+    constexpr bool satfold = SBP_B3_SATFOLD && SAT == 1 && HELP && SBP_B3_EXP == 0;
     const bool XTc = HELP && FUSED && cbnz;  // = XT
     // (measured and dropped: -b_j g_j as the accumulators' initial value, one DFMA per SAT entry after the chain instead of DADD +
     // DFMA: config 3 0.3095 vs 0.2929 ms; two instead of three FP64 instructions per entry in stage updates without an extra
@@ -745,6 +751,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             };
             if (SAT == 1 && mask) {  // du_j += b_j (u_j - g_j); the chunk's own rows are inside its window
                 const uint32_t o0 = ring_elem(r0w), o1 = ring_elem(r0w + 1);
+                const double sbx = (FUSED && satfold) ? sb.x * p.ch : sb.x, sby = (FUSED && satfold) ? sb.y * p.ch : sb.y;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     if (p.g_stride != 0) {  // per-instance boundary data
@@ -753,8 +760,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         if (mask & 1) gs0 = __ldg(p.g + (paired ? 2 * row + h0 : row) * p.g_stride + n0);
                         if (mask & 2) gs1 = __ldg(p.g + (paired ? 2 * row + h1 : row) * p.g_stride + n1);
                     }
-                    if (mask & 1) acc[mt][0] += sb.x * (*reinterpret_cast<const double*>(su_lane + o0 + mt * MTB) - gs0);
-                    if (mask & 2) acc[mt][1] += sb.y * (*reinterpret_cast<const double*>(su_lane + o1 + mt * MTB) - gs1);
+                    if (satfold) {  // b_j u_j is part of the chain: -b_j g_j remains (times ch in a stage update)
+                        if (mask & 1) acc[mt][0] = fma(-sbx, gs0, acc[mt][0]);
+                        if (mask & 2) acc[mt][1] = fma(-sby, gs1, acc[mt][1]);
+                    } else {
+                        if (mask & 1) acc[mt][0] += sb.x * (*reinterpret_cast<const double*>(su_lane + o0 + mt * MTB) - gs0);
+                        if (mask & 2) acc[mt][1] += sb.y * (*reinterpret_cast<const double*>(su_lane + o1 + mt * MTB) - gs1);
+                    }
                 }
             }
             if (SAT == 2 && I.flags != 0) {
@@ -815,8 +827,12 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (with_extra) e = XTc ? *reinterpret_cast<const double2*>(sq + mt * 32) : ex[(FUSED && !HELP) ? mt : 0];
                     const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
                     const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
-                    acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
-                    acc[mt][1] = fma(p.ch, acc[mt][1], fma(p.ca, u1, p.cb * e.y));
+                    if (satfold) {  // the image is ch (A - B) - ca I: only the extra operand is left
+                        if (cbnz) acc[mt][0] = fma(p.cb, e.x, acc[mt][0]), acc[mt][1] = fma(p.cb, e.y, acc[mt][1]);
+                    } else {
+                        acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
+                        acc[mt][1] = fma(p.ch, acc[mt][1], fma(p.ca, u1, p.cb * e.y));
+                    }
                 }
             }
         }
@@ -963,6 +979,13 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
 #undef SBP_BSR3_OUT
 }
 
+// image of a stage update: ch * (A - B) - ca * I in fragment form (the chain, run with alpha = -1, then yields ca u - ch (A - B) u)
+__global__ void k_stage_image(double* __restrict__ out, const double* __restrict__ in, const unsigned char* __restrict__ mask,
+                              long long n, double ch, double ca) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ch * in[i] - (mask[i] ? ca : 0.0);
+}
+
 // p arrives filled in by launch_bsr (operator, batch view, SAT data); returns false when this kernel does not apply
 bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int out, int32_t* rc) {
     // option bsr_v3 (SBP_BSR_V3): 0 = k_bsr, 1 = this kernel for large batches, 2 = always
@@ -985,6 +1008,8 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     // (measured: 2D RHS N = 1296 0.362 ms per stage with the extra operand against 0.414 on k_bsr; 1D RHS N = 101 0.279 against
     // 0.240 -> those stay on k_bsr)
     if (p.fused && (cw != 9 || satmode == 0 || (satmode == 2 && p.cb != 0.0 && enabled != 2))) return false;
+    // the helper kernels with 2D SATs are compiled for the folded image A - diag(b) (needs alpha * scale = -1: the RHS entry points)
+    if (SBP_B3_SATFOLD && SBP_B3_EXP == 0 && satmode == 1 && cw == 9 && (!p.val_sat || p.alpha != -1.0)) return false;
     const long long B = p.B;
     // the largest tile with one chunk of lookahead that still gives every SM work, then the deepest ring that fits
     int MT = 8;
@@ -1003,14 +1028,25 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const size_t smem = bsr3_smem(op, MT, D, out, cw);
     p.skew = ctx->tune[T_BSR_SKEW];
     p.sem = ctx->tune[T_BSR_SEM];
+    // 2D SATs with the u-term folded into the operator image (SBP_B3_SATFOLD; needs alpha * scale = -1: the RHS entry points)
+    if (SBP_B3_SATFOLD && SBP_B3_EXP == 0 && satmode == 1 && cw == 9) {
+        p.satfold = 1;
+        p.val = p.val_sat;
+        if (p.fused) {
+            k_stage_image<<<(unsigned)((p.nvals + 255) / 256), 256, 0, ctx->stream>>>(p.val_stage, p.val_sat, p.diagmask, p.nvals,
+                                                                                       p.ch, p.ca);
+            ctx->launches++;
+            p.val = p.val_stage;
+        }
+    }
     // L2 prefetch distance of the box producer: 5 boxes ahead when a tile row is much longer than the ring (2D clouds: config 3
     // 0.312 -> 0.291 ms, N = 900 / 1936 -5 / -4 %); banded 1D operators, whose ring holds most of the row, lose 6-13 % with any
     // prefetch (profiles/r2_bsr_notes.txt)
     p.pf = std::min(ctx->tune[T_BSR_PF] >= 0 ? ctx->tune[T_BSR_PF] : (p.nbt > 2 * p.nbox ? 5 : 0), p.nbt - 1);
     const bool verbose = ctx->tune[T_BSR_VERBOSE] != 0;
     if (verbose)
-        fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d cw=%d\n",
-                p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out, cw);
+        fprintf(stderr, "k_bsr3: N=%d B=%lld nrb=%d nch=%d frags=%lld maxnf=%d MT=%d depth=%d nbox=%d smem=%zu sat=%d out=%d cw=%d satfold=%d fused=%d\n",
+                p.N, B, p.nrb, p.nch, (long long)op->bsr_frags, op->bsr_maxnf, MT, D, p.nbox, smem, satmode, out, cw, p.satfold, p.fused);
     switch (MT) {
         case 8: *rc = launch_bsr3_mt<8>(ctx, p, smem, satmode, out, cw); break;
         case 7: *rc = launch_bsr3_mt<7>(ctx, p, smem, satmode, out, cw); break;

@@ -155,6 +155,7 @@ struct sbp_op {
     int bsr_nrb = 0;
     int bsr_N = 0;                // row length the block-sparse image works on: N, or 2N for odd N (instance pairs, see build_bsr)
     std::vector<int> bsr_rows;    // host copy: first rows of the two quads of every row block (2 * nrb)
+    std::vector<int> bsr_diag;    // host copy: index into d_bsr_val of the diagonal entry of every block row (8 * nrb, -1: row >= N)
     int bsr_nbox[sbp::kBsrDepths] = {};  // ring size (boxes) that allows d chunks of lookahead, d = 0..kBsrDepths-1
     int bsr_maxf = 0;             // most fragments of a chunk
     int bsr_maxnf = 0;            // most fragments of a row block
@@ -169,6 +170,11 @@ struct sbp_op {
     double* d_a = nullptr;
     double* d_q_consts = nullptr;  // per-node constants for the analysis quantities
     double* d_rb_bdiag = nullptr;  // 2D bundle over a block-sparse operator: b_j of every block row (block order), 0 = no SAT
+    // the same bundle with the SAT's u-term folded into the operator: fragments of A - diag(b) (du = -(A - B) u - B g), a scratch
+    // image for stage updates (ch (A - B) - ca I, rebuilt per launch) and the 0/1 mask of the diagonal entries
+    double* d_bsr_val_sat = nullptr;
+    double* d_bsr_val_stage = nullptr;
+    unsigned char* d_bsr_diagmask = nullptr;
     double sat_a0 = 1.0, sat_aN = 1.0, sat_w0 = 1.0, sat_wN = 1.0;  // 1D bundle: end speeds and end weights
 };
 
