@@ -147,7 +147,7 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 // HELP: four extra warps issue the TMA stores (helper h serves consumer warps h and h + 4): a consumer warp deposits its
 // accumulators in its staging buffer and signals an mbarrier instead of issuing the stores and waiting for the buffer itself.
 // FUSED: Runge-Kutta stage update on the finished RHS (sbp_rhs_advection*_stage), as in k_bsr<..., FUSED>.
-template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false>
 __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
            const __grid_constant__ CUtensorMap tmap_ex, const __grid_constant__ CUtensorMap tmap_out8) {
@@ -180,7 +180,9 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     __shared__ int gate[4];     // SBP_B3_GATE: id of the warp inside the gated part of its chain, -1: open
     __shared__ int sem_fin[4];  // CW == 12, p.sem: chains finished per scheduler (at most two of its three warps multiply at a time)
     // XT: the extra operand of a fused stage update travels through the staging buffers (TMA loads issued by the helpers)
-    const bool XT = HELP && FUSED && p.cb != 0.0;
+    // (XTRA: the launch has an extra operand with cb != 0 -- a template parameter, so that stage updates without one carry none of
+    // the machinery: the runtime form of this flag cost 2-7 % in the same way as a runtime SAT fold, profiles/r2_bsr_notes.txt 8)
+    constexpr bool XT = HELP && FUSED && XTRA;
     static_assert(!HELP || (CW == kBsrCH && OUT == 2 && kBsrCH % 4 == 0), "helper warps: one consumer warp per row block of a chunk, TMA output");
     double* s_u = smem;                                                              // nbox * BOX
     double* s_val = s_u + (size_t)p.nbox * BOX;                                      // nst * maxf * 32
@@ -486,13 +488,15 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // (routed through a shuffle: ptxas does not rematerialise a shuffle result from the constant bank)
     auto pin = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
     const int nch = nch_p, Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
-    const int scale_needed = pin(alpha_m1 ? 0 : 1);
+    // the launcher gives SAT == 1 helper kernels the folded image (or does not take this kernel at all)
+    constexpr bool satfold = SBP_B3_SATFOLD && SAT == 1 && HELP && SBP_B3_EXP == 0;
+    // boundary data per instance (g_stride != 0): a template parameter (GPI) of the kernels with the folded image, a runtime test elsewhere
+    const bool g_per_inst = satfold ? GPI : p.g_stride != 0;
+    const int scale_needed = satfold ? 0 : pin(alpha_m1 ? 0 : 1);  // (the folded image is only used with alpha = -1)
     // comparisons of double parameters, made once: a DSETP inside the item loop queues behind the DMMAs of the other warp (ncu: 4 %
     // of the fused kernel's samples on five of them per block)
     const int cbnz = pin(p.cb != 0.0 ? 1 : 0);
-    // the launcher gives SAT == 1 helper kernels the folded image (or does not take this kernel at all)
-    constexpr bool satfold = SBP_B3_SATFOLD && SAT == 1 && HELP && SBP_B3_EXP == 0;
-    const bool XTc = HELP && FUSED && cbnz;  // = XT
+    constexpr bool XTc = XT;
     // (measured and dropped: -b_j g_j as the accumulators' initial value, one DFMA per SAT entry after the chain instead of DADD +
     // DFMA: config 3 0.3095 vs 0.2929 ms; two instead of three FP64 instructions per entry in stage updates without an extra
     // operand: SSPRK53 step 1.658 vs 1.622 ms)
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         I.h0 = (paired && I.r0w >= Nh) ? 1 : 0, I.h1 = (paired && I.r0w + 1 >= Nh) ? 1 : 0;
         I.n0 = I.r0w - I.h0 * Nh, I.n1 = I.r0w + 1 - I.h1 * Nh;
         I.gs0 = 0.0, I.gs1 = 0.0;
-        if (SAT == 1 && I.mask && p.g_stride == 0) {
+        if (SAT == 1 && I.mask && !g_per_inst) {
             if (I.mask & 1) I.gs0 = __ldg(p.g + I.n0);
             if (I.mask & 2) I.gs1 = __ldg(p.g + I.n1);
         }
@@ -614,7 +618,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         for (int mt = 0; mt < MT; mt++) acc[mt][0] = acc[mt][1] = 0.0;
         // stage update: the lane's entries of `extra` are requested now and consumed after the chain
         double2 ex[(FUSED && !HELP) ? MT : 1];  // (with helper warps the operand comes through the staging buffer: XT)
-        const bool with_extra = FUSED && cbnz && active && r0w < Nr;
+        const bool with_extra = FUSED && (HELP ? XTRA : cbnz != 0) && active && r0w < Nr;
         if (FUSED && !HELP && with_extra) {
             const int nbx = min(Bir - b0, TI);
 #pragma unroll
@@ -754,7 +758,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 const double sbx = (FUSED && satfold) ? sb.x * p.ch : sb.x, sby = (FUSED && satfold) ? sb.y * p.ch : sb.y;
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
-                    if (p.g_stride != 0) {  // per-instance boundary data
+                    if (g_per_inst) {  // per-instance boundary data
                         const int il = 8 * mt + g;
                         const long long row = b0c + (il < nb ? il : 0);
                         if (mask & 1) gs0 = __ldg(p.g + (paired ? 2 * row + h0 : row) * p.g_stride + n0);
@@ -828,7 +832,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
                     const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
                     if (satfold) {  // the image is ch (A - B) - ca I: only the extra operand is left
-                        if (cbnz) acc[mt][0] = fma(p.cb, e.x, acc[mt][0]), acc[mt][1] = fma(p.cb, e.y, acc[mt][1]);
+                        if (XTRA) acc[mt][0] = fma(p.cb, e.x, acc[mt][0]), acc[mt][1] = fma(p.cb, e.y, acc[mt][1]);
                     } else {
                         acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
                         acc[mt][1] = fma(p.ch, acc[mt][1], fma(p.ca, u1, p.cb * e.y));
@@ -933,9 +937,9 @@ static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int o
     return bsr3_smem(op, MT, D, out, cw) + 1024 <= (size_t)ctx->smem_optin;
 }
 
-template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false>
 static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP, FUSED>;
+    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP, FUSED, XTRA, GPI>;
     constexpr int TI = 8 * MT;
     constexpr int THREADS = (CW + 2 + (HELP ? 4 : 0)) * 32;
     CUtensorMap tmap, tmap_out;
@@ -970,9 +974,14 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
         default: return launch_bsr3_k<MT, S, 0, kBsrCH>(ctx, p, smem);                                     \
     }
     if (p.fused) {  // stage updates: RHS launches with TMA output and store helpers (checked by launch_bsr3)
-        if (sat == 1) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, true>(ctx, p, smem);
-        return launch_bsr3_k<MT, 2, 2, kBsrCH, true, true>(ctx, p, smem);
+        const bool xtra = p.extra != nullptr && p.cb != 0.0;
+        if (sat == 1 && p.g_stride != 0)
+            return xtra ? launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, true, true>(ctx, p, smem)
+                        : launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, false, true>(ctx, p, smem);
+        if (sat == 1) return xtra ? launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, true>(ctx, p, smem) : launch_bsr3_k<MT, 1, 2, kBsrCH, true, true>(ctx, p, smem);
+        return xtra ? launch_bsr3_k<MT, 2, 2, kBsrCH, true, true, true>(ctx, p, smem) : launch_bsr3_k<MT, 2, 2, kBsrCH, true, true>(ctx, p, smem);
     }
+    if (sat == 1 && out == 2 && cw == 9 && p.g_stride != 0) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, false, false, true>(ctx, p, smem);
     if (sat == 1) { SBP_BSR3_OUT(1) }
     if (sat == 2) { SBP_BSR3_OUT(2) }
     SBP_BSR3_OUT(0)
