@@ -469,10 +469,16 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     Rec r0 = load_rec(kBsrCH * pc + ps);
     advance();
     int skip = warp / kBsrCH, myslot = warp % kBsrCH;  // items to pass before this warp's next block; its slot there
-    double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0;
+    double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0, sat_c0 = 0.0, sat_cN = 0.0;
+    // boundary data per instance: a template parameter (GPI) of the helper kernels, a runtime test elsewhere
+    const bool bc_per_inst = (SAT == 2 && HELP) ? GPI : p.sat.bc_stride != 0;
     if (SAT == 2) {
         sat_iw0 = 1.0 / p.sat.w0, sat_iwN = 1.0 / p.sat.wN;
         if (p.sat.bc_stride == 0) sat_lb = __ldg(p.sat.bc), sat_rb = __ldg(p.sat.bc + 1);
+        // left boundary: inflow (a0 > 0) contributes a0 (lb - u) / w0, outflow nothing; right boundary: aN < 0 contributes
+        // -aN (rb - u) / wN -- the comparisons are made here, once (sat_c0 / sat_cN = coefficient of (bc - u), 0: no term)
+        sat_c0 = p.sat.a0 > 0.0 ? p.sat.a0 * sat_iw0 : 0.0;
+        sat_cN = p.sat.aN > 0.0 ? 0.0 : -p.sat.aN * sat_iwN;
     }
     // loop invariants the compiler would otherwise rematerialise at every use: pinned in registers
     int sgn = alpha_m1 ? (int)0x80000000u : 0;
@@ -796,20 +802,14 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                             const double u = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_u) + o +
                                                                               (size_t)il * (BX * 8));
                             double lb = sat_lb, rbv = sat_rb;
-                            if (p.sat.bc_stride != 0) {  // per-instance boundary data
+                            if (bc_per_inst) {  // per-instance boundary data
                                 if (left) lb = __ldg(p.sat.bc + inst * p.sat.bc_stride);
                                 if (right) rbv = __ldg(p.sat.bc + inst * p.sat.bc_stride + 1);
                             }
                             // (f - a u) / w as in sat1d_left/right, with the division replaced by the reciprocal weight
                             double v = 0.0;
-                            if (left) {
-                                const double t0 = p.sat.a0 * u;
-                                v += ((p.sat.a0 > 0.0 ? p.sat.a0 * lb : t0) - t0) * sat_iw0;
-                            }
-                            if (right) {
-                                const double tN = p.sat.aN * u;
-                                v -= ((p.sat.aN > 0.0 ? tN : p.sat.aN * rbv) - tN) * sat_iwN;
-                            }
+                            if (left) v = sat_c0 * (lb - u);
+                            if (right) v = fma(sat_cN, rbv - u, v);
                             sv2[kk] = v;
                         }
                     }
@@ -980,9 +980,13 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
             return xtra ? launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, true, true>(ctx, p, smem)
                         : launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, false, true>(ctx, p, smem);
         if (sat == 1) return xtra ? launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, true>(ctx, p, smem) : launch_bsr3_k<MT, 1, 2, kBsrCH, true, true>(ctx, p, smem);
+        if (p.sat.bc_stride != 0)
+            return xtra ? launch_bsr3_k<MT, 2, 2, kBsrCH, true, true, true, true>(ctx, p, smem)
+                        : launch_bsr3_k<MT, 2, 2, kBsrCH, true, true, false, true>(ctx, p, smem);
         return xtra ? launch_bsr3_k<MT, 2, 2, kBsrCH, true, true, true>(ctx, p, smem) : launch_bsr3_k<MT, 2, 2, kBsrCH, true, true>(ctx, p, smem);
     }
     if (sat == 1 && out == 2 && cw == 9 && p.g_stride != 0) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, false, false, true>(ctx, p, smem);
+    if (sat == 2 && out == 2 && cw == 9 && p.sat.bc_stride != 0) return launch_bsr3_k<MT, 2, 2, kBsrCH, true, false, false, true>(ctx, p, smem);
     if (sat == 1) { SBP_BSR3_OUT(1) }
     if (sat == 2) { SBP_BSR3_OUT(2) }
     SBP_BSR3_OUT(0)
