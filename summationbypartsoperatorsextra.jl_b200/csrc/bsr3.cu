@@ -469,6 +469,13 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     Rec r0 = load_rec(kBsrCH * pc + ps);
     advance();
     int skip = warp / kBsrCH, myslot = warp % kBsrCH;  // items to pass before this warp's next block; its slot there
+    // the launcher gives SAT == 1 helper kernels the folded image (or does not take this kernel at all)
+    constexpr bool satfold = SBP_B3_SATFOLD && SAT == 1 && HELP && SBP_B3_EXP == 0;
+    // boundary data per instance (g_stride != 0): a template parameter (GPI) of the kernels with the folded image, a runtime test elsewhere
+    const bool g_per_inst = satfold ? GPI : p.g_stride != 0;
+    // stage updates of the helper kernels run on an image that contains ca I and the factor ch (2D: ch (A - B) - ca I with
+    // alpha = -1; 1D: ch alpha D + ca I with alpha = +1): after the chain only cb * extra and the SAT constants are left
+    constexpr bool stagefold = FUSED && HELP && SBP_B3_SATFOLD && SBP_B3_EXP == 0 && (SAT == 1 || SAT == 2);
     double sat_iw0 = 0.0, sat_iwN = 0.0, sat_lb = 0.0, sat_rb = 0.0, sat_c0 = 0.0, sat_cN = 0.0;
     // boundary data per instance: a template parameter (GPI) of the helper kernels, a runtime test elsewhere
     const bool bc_per_inst = (SAT == 2 && HELP) ? GPI : p.sat.bc_stride != 0;
@@ -479,6 +486,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
         // -aN (rb - u) / wN -- the comparisons are made here, once (sat_c0 / sat_cN = coefficient of (bc - u), 0: no term)
         sat_c0 = p.sat.a0 > 0.0 ? p.sat.a0 * sat_iw0 : 0.0;
         sat_cN = p.sat.aN > 0.0 ? 0.0 : -p.sat.aN * sat_iwN;
+        if (stagefold) sat_c0 *= p.ch, sat_cN *= p.ch;
     }
     // loop invariants the compiler would otherwise rematerialise at every use: pinned in registers
     int sgn = alpha_m1 ? (int)0x80000000u : 0;
@@ -494,10 +502,6 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // (routed through a shuffle: ptxas does not rematerialise a shuffle result from the constant bank)
     auto pin = [](int v) { return __shfl_sync(0xffffffffu, v, 0); };
     const int nch = nch_p, Nr = pin(N), nstr = pin(nst), tstepr = pin(tstep), ntlr = pin(ntl), Bir = pin(Bi);
-    // the launcher gives SAT == 1 helper kernels the folded image (or does not take this kernel at all)
-    constexpr bool satfold = SBP_B3_SATFOLD && SAT == 1 && HELP && SBP_B3_EXP == 0;
-    // boundary data per instance (g_stride != 0): a template parameter (GPI) of the kernels with the folded image, a runtime test elsewhere
-    const bool g_per_inst = satfold ? GPI : p.g_stride != 0;
     // the image arrives scaled: alpha = +-1 (sign flip of the B operand), any other alpha through k_stage_image in front of the launch
     constexpr int scale_needed = 0;
     // comparisons of double parameters, made once: a DSETP inside the item loop queues behind the DMMAs of the other warp (ncu: 4 %
@@ -832,7 +836,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     if (with_extra) e = XTc ? *reinterpret_cast<const double2*>(sq + mt * 32) : ex[(FUSED && !HELP) ? mt : 0];
                     const double u0 = *reinterpret_cast<const double*>(su_lane + o0 + mt * MTB);
                     const double u1 = *reinterpret_cast<const double*>(su_lane + o1 + mt * MTB);
-                    if (satfold) {  // the image is ch (A - B) - ca I: only the extra operand is left
+                    if (stagefold) {  // only the extra operand is left
                         if (XTRA) acc[mt][0] = fma(p.cb, e.x, acc[mt][0]), acc[mt][1] = fma(p.cb, e.y, acc[mt][1]);
                     } else {
                         acc[mt][0] = fma(p.ch, acc[mt][0], fma(p.ca, u0, p.cb * e.x));
@@ -1042,6 +1046,30 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const size_t smem = bsr3_smem(op, MT, D, out, cw);
     p.skew = ctx->tune[T_BSR_SKEW];
     p.sem = ctx->tune[T_BSR_SEM];
+    if (SBP_B3_SATFOLD && SBP_B3_EXP == 0 && p.fused && satmode == 2 && cw == 9) {
+        // 1D stage update: image ch alpha D + ca I (diagonal mask of the operator uploaded at first use), run with alpha = +1
+        sbp_op* mop = const_cast<sbp_op*>(op);
+        const long long nv = (long long)op->bsr_frags * 32;
+        if (!mop->d_bsr_diagmask) {
+            std::vector<unsigned char> mask((size_t)nv, 0);
+            for (int k : op->bsr_diag)
+                if (k >= 0) mask[k] = 1;
+            if (cudaMalloc(&mop->d_bsr_diagmask, (size_t)nv) != cudaSuccess ||
+                cudaMemcpy(mop->d_bsr_diagmask, mask.data(), (size_t)nv, cudaMemcpyHostToDevice) != cudaSuccess) {
+                *rc = SBP_ENOMEM;
+                return true;
+            }
+        }
+        if (!mop->d_bsr_val_stage && cudaMalloc(&mop->d_bsr_val_stage, (size_t)nv * 8) != cudaSuccess) {
+            *rc = SBP_ENOMEM;
+            return true;
+        }
+        k_stage_image<<<(unsigned)((nv + 255) / 256), 256, 0, ctx->stream>>>(mop->d_bsr_val_stage, p.val, mop->d_bsr_diagmask, nv,
+                                                                             p.ch * p.alpha, -p.ca);
+        ctx->launches++;
+        p.val = mop->d_bsr_val_stage;
+        p.alpha = 1.0;
+    }
     // alpha other than +-1: the launch runs on a scaled copy of the image (3 us) instead of multiplying 14 accumulators per block
     if (p.alpha != 1.0 && p.alpha != -1.0 && !(SBP_B3_SATFOLD && satmode == 1 && cw == 9)) {
         sbp_op* mop = const_cast<sbp_op*>(op);  // scratch of the operator (launches of a context are stream-ordered)
