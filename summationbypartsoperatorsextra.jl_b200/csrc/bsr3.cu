@@ -71,6 +71,10 @@
 #define SBP_B3_SATFOLD 1  // 1: 2D RHS / stage launches of the helper kernel run on the image of A - diag(b) (stage updates: ch (A - B) - ca I,
 #endif                    // rebuilt by k_stage_image per launch): no ring loads and one FP64 instruction less per SAT entry, no
                           // ca * u term and no scaling by ch after the chain
+#ifndef SBP_B3_XPF
+#define SBP_B3_XPF 0  // 1: the store helpers prefetch the extra operand of a stage update into L2 two items ahead
+                      // (measured: stage with extra operand 0.355 -> 0.442 ms on config 3 -- the prefetches of quads compete with the box stream)
+#endif
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -273,6 +277,22 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     // first tensor row of the next item (same tile, or this CTA's next tile); -1: there is none
                     const long long ntile = cc + 1 < p.nch ? tile : tile + gridDim.x;
                     const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
+                    if (XT && SBP_B3_XPF) {  // L2 prefetch of the extra operand's quads two items ahead (the loads below are one ahead)
+                        const int cn2 = cn + 1 < p.nch ? cn + 1 : 0;
+                        const long long t2 = cn2 == 0 ? ntile + gridDim.x : ntile;  // tile of the item after next
+                        if (t2 < ntiles)
+                            for (int k = 0; k < KH; k++) {
+                                const int4 a = __ldg(rec + 2 * (kBsrCH * cn2 + h + 4 * k));
+                                if (a.z < N)
+                                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(&tmap_ex),
+                                                 "r"(a.z), "r"((int)(t2 * TI))
+                                                 : "memory");
+                                if (a.z < N && a.w < N)
+                                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(&tmap_ex),
+                                                 "r"(a.w), "r"((int)(t2 * TI))
+                                                 : "memory");
+                            }
+                    }
                     for (int k = 0; k < KH; k++) {
                         const int w = h + 4 * k;
                         B3_PARK(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
