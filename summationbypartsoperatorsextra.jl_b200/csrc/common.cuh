@@ -45,7 +45,7 @@ constexpr int kBsrBX = SBP_BSR_BX;     // nodes per TMA box: 4 (mod 16) doubles 
 constexpr int kBsrCH = SBP_BSR_CH;     // row blocks per chunk
 constexpr int kBsrGroups = SBP_BSR_G;  // consumer groups, alternating chunks
 constexpr int kBsrDepths = 8;          // pipeline depths (chunks of lookahead) the host prepares ring sizes / records for
-static_assert(kBsrBX % 16 == 4, "box rows must be 4 (mod 16) doubles");
+static_assert(kBsrBX % 16 == 4 || kBsrBX % 16 == 12, "box rows must be 4 or 12 (mod 16) doubles: instance g then starts at bank 8g (or -8g) mod 32");
 constexpr int kMaxSmallN = 128;  // smem-resident DMMA path handles N <= 128 (16 n-tiles of 8 rows)
 
 // Tuning / debugging knobs.  Each is read from its environment variable ONCE, when a context is created, and can be changed
