@@ -1031,8 +1031,11 @@ def test_rhs_advection1d_odd_N_per_instance_bc(ctx, N, B, bsr_generation):
 # ---- Runge-Kutta stage updates riding on the RHS pass (sbp_rhs_advection*_stage) ---------------------
 @pytest.mark.parametrize("n1,storage", [(12, "sparse"), (9, "sparse"), (12, "dense")])  # N = 144 even, 81 odd (pairs), dense fallback
 @pytest.mark.parametrize("B", [1, 2, 65, 1027])
-@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("fused", ["1", "0", "helper kernel"])
 def test_stage_update_advection2d(ctx, n1, storage, B, fused):
+    if fused == "helper kernel":  # small batches would take k_bsr: force the kernel large batches get (folded operator image,
+        ctx.set_option("bsr_v3", 2)  # stage image per launch, extra operand / per-instance g as template parameters)
+        fused = "1"
     ctx.set_option("fused_stage", int(fused))
     D = _scattered_mfsbp(n1, seed=5)
     a = (0.6, -1.0)
@@ -1060,8 +1063,11 @@ def test_stage_update_advection2d(ctx, n1, storage, B, fused):
 
 @pytest.mark.parametrize("N,storage", [(101, "sparse"), (104, "sparse"), (64, "dense")])
 @pytest.mark.parametrize("B", [1, 3, 130, 1030])
-@pytest.mark.parametrize("fused", ["1", "0"])
+@pytest.mark.parametrize("fused", ["1", "0", "helper kernel"])
 def test_stage_update_advection1d(ctx, N, storage, B, fused):
+    if fused == "helper kernel":  # the kernel large batches get (stage image ch alpha D + ca I, per-instance bc as a template parameter)
+        ctx.set_option("bsr_v3", 2)
+        fused = "1"
     ctx.set_option("fused_stage", int(fused))
     D = S.mattsson_nordstrom_2004(4, 0.0, 1.0, N)
     D.storage = storage
