@@ -310,6 +310,8 @@ def test_apply_sparse_1d(ctx, order, N, B, sparse_kernel):
     dv = ctx.upload(Y0)
     S.mul_(dv, D, ctx.upload(U), 0.5, -2.0)
     assert rel_err(dv.to_host(), O.apply_batch(Do.matrix(), U, 0.5, -2.0, Y0)) <= TOL
+    S.mul_(dv, D, ctx.upload(U), -0.37, 0.0)  # beta = 0: TMA output; alpha other than +-1: prescaled operator image (bsr3.cu)
+    assert rel_err(dv.to_host(), O.apply_batch(Do.matrix(), U, -0.37)) <= TOL
 
 
 @pytest.mark.parametrize("N,nnz_row,B", [(8, 3, 5), (37, 6, 129), (250, 9, 77), (1000, 12, 300), (1001, 12, 300),
