@@ -20,7 +20,7 @@ const TuneSpec kTuneSpec[T_COUNT] = {
     {"bsr_mh", "SBP_BSR_MH", 0},            {"bsr_v3", "SBP_BSR_V3", -1},                {"bsr_cw", "SBP_BSR_CW", 8},
     {"bsr_help", "SBP_BSR_HELP", 1},        {"bsr_skew", "SBP_BSR_SKEW", 0},             {"bsr_sem", "SBP_BSR_SEM", 0},
     {"bsr_pf", "SBP_BSR_PF", -1},           {"bsr_verbose", "SBP_BSR_VERBOSE", 0},       {"gemm_variant", "SBP_GEMM_VARIANT", -2},
-    {"ds_v4", "SBP_DS_V4", 1},              {"sparse_db", "SBP_SPARSE_DB", 0}};
+    {"ds_v4", "SBP_DS_V4", 1},              {"sparse_db", "SBP_SPARSE_DB", 0},           {"bsr_pair8", "SBP_BSR_PAIR8", -1}};
 
 static void tune_from_env(sbp_ctx* ctx) {
     for (int k = 0; k < T_COUNT; k++) {
@@ -548,6 +548,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     // {first fragment relative to the chunk, fragments, first row of quad A, of quad B | ring slot of the chunk's lowest
     // box (blo % nbox[d]), blo, 0, 0}; padded to whole chunks with inactive records (rows >= N, no fragments)
     std::vector<int> item((size_t)kBsrDepths * nch * CH * 8, 0);
+    int pairs = 0;
     for (int d = 0; d < kBsrDepths; d++)
         for (int rb = 0; rb < nch * CH; rb++) {
             int* e = &item[((size_t)d * nch * CH + rb) * 8];
@@ -555,7 +556,15 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
                 for (int k = 0; k < 4; k++) e[k] = rbmeta[4 * rb + k];
                 e[4] = blo[rb / CH] % op->bsr_nbox[d];
                 e[5] = blo[rb / CH];
-                e[7] = rbf[rb];  // absolute first fragment (bsr3.cu reads the fragments straight from the image)
+                // pair flag (bsr3.cu): blocks 2j, 2j + 1 of a chunk whose quads are x-neighbours (A next to A, B next to B) are staged
+                // side by side and leave as two {8 x instances} boxes instead of four {4 x instances}: 1 = left block, 2 = right block
+                {
+                    const int l = rb & ~1, r = l + 1;
+                    const bool self_l = rows[2 * l + 1] == rows[2 * l] + 4;
+                    if (r < nrb && !self_l && rows[2 * r + 1] != rows[2 * r] + 4 && rows[2 * r] == rows[2 * l] + 4 &&
+                        rows[2 * r + 1] == rows[2 * l + 1] + 4 && rows[2 * r + 1] + 4 <= N && rows[2 * l + 1] < N)
+                        e[7] = rb == l ? 1 : 2, pairs += d == 0;
+                }
                 // rows of the block that carry a 1D SAT: bit k = block row k is node 0 of its instance, bit 8 + k = node N1 - 1
                 for (int k = 0; k < 8; k++) {
                     const int r = block_row(rb, k);
@@ -587,6 +596,7 @@ static int32_t build_bsr(sbp_op* op, int N1, const std::vector<int>& rowptr1, co
     op->bsr_nrb = nrb;
     op->bsr_rows = rows;
     op->bsr_diag = diag;
+    op->bsr_pairs = pairs;
     op->bsr_frags = (int64_t)frag.size() / 32;
     if (frag.empty()) {
         frag.assign(32, 0.0);

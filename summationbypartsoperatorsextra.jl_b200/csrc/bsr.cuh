@@ -32,7 +32,8 @@ struct BsrParams {
     double* val_stage = nullptr;
     const unsigned char* diagmask = nullptr;
     long long nvals = 0;
-    int satfold = 0;                  // 1: the image in `val` contains the fold (set by launch_bsr3)
+    int satfold = 0;
+    int pair8 = 0;                    // 1: pair-flagged blocks are stored as {8 x instances} boxes; the two warps of a scheduler take neighbouring slots                  // 1: the image in `val` contains the fold (set by launch_bsr3)
     int sem = 0;                      // bsr3.cu, 12 consumer warps: at most `sem` of the three warps of a scheduler multiply at a time (0: off)
     // fused 2D SAT: du_j += b_j (u_j - g_j) on inflow rows
     const double* __restrict__ rb_bdiag;  // [nrb][8] b_j of the block's rows in block order, 0 on non-inflow rows

@@ -75,6 +75,10 @@
 #define SBP_B3_XPF 0  // 1: the store helpers prefetch the extra operand of a stage update into L2 two items ahead
                       // (measured: stage with extra operand 0.355 -> 0.442 ms on config 3 -- the prefetches of quads compete with the box stream)
 #endif
+#ifndef SBP_B3_PAIR8
+#define SBP_B3_PAIR8 1  // 1: x-neighbouring blocks 2j, 2j + 1 of a chunk (record flag) are staged side by side, [instance][8 nodes] per
+#endif                  // quad row, and stored as two {8 x instances} boxes instead of four {4 x instances}: the what-if "same bytes in
+                        // half the store boxes" was worth 12 % on config 3 (0.2826 -> 0.2487 ms)
 #ifndef SBP_B3_PARKED
 #define SBP_B3_PARKED 0  // 1: producers and store helpers wait with a suspend-time hint instead of tight polling (measured: no effect)
 #endif
@@ -158,6 +162,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // MERGE8: adjacent quads of a block are staged as [instance][8 rows] and stored by one box (not when the staging buffer also
     // carries the extra operand of a fused stage update, which arrives quad by quad)
     constexpr bool MERGE8 = SBP_B3_MERGE8 && HELP && SBP_B3_EXP == 0;
+    // PAIR8: the same for two x-neighbouring blocks (not with an extra operand in the staging buffers)
+    constexpr bool PAIR8 = SBP_B3_PAIR8 && MERGE8 && kBsrCH == 8 && !(FUSED && XTRA);
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
     constexpr int TI = 8 * MT;
@@ -249,12 +255,17 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             int trh = 0;
 #endif
             const int4* rec = p.item;
-            constexpr int KH = kBsrCH / 4;  // consumer warps served by one helper (h, h + 4, ...)
-            int rowA[KH], rowB[KH];
+            constexpr int KH = kBsrCH / 4;  // consumer warps served by one helper
+            // slots of this helper's blocks: h, h + 4, ... -- or, with pairs (p.pair8), the neighbouring slots KH h, KH h + 1, ...;
+            // either way they belong to the two warps of one scheduler (see `slot` in the consumer part)
+            const bool pm = PAIR8 && p.pair8;
+            auto hslot = [&](int k) { return pm ? KH * h + k : h + 4 * k; };
+            int rowA[KH], rowB[KH], pairf = 0;
             for (int k = 0; k < KH; k++) {
-                const int4 a = __ldg(rec + 2 * (h + 4 * k));
+                const int4 a = __ldg(rec + 2 * hslot(k));
                 rowA[k] = a.z, rowB[k] = a.w;
             }
+            if (pm) pairf = __ldg(rec + 2 * (KH * h) + 1).w;  // 1: the helper's first two blocks form a pair in this item
             // XT: quads rA / rB of `extra` for tensor rows y.. of consumer warp w -> its staging buffer, completion on ext_full[w]
             auto load_extra = [&](int w, int rA, int rB, int y) {
                 double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
@@ -264,16 +275,17 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                 if (rA < N && rB < N) tma_load_2d(so + 8 * MT * 4, &tmap_ex, rB, y, &ext_full[w]);
             };
             if (XT && (long long)blockIdx.x < ntiles)
-                for (int k = 0; k < KH; k++) load_extra(h + 4 * k, rowA[k], rowB[k], (int)(blockIdx.x * TI));
+                for (int k = 0; k < KH; k++) load_extra(hslot(k), rowA[k], rowB[k], (int)(blockIdx.x * TI));
             for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b0 = (int)(tile * TI);
                 for (int cc = 0; cc < p.nch; cc++) {
                     const int cn = c + 1 < p.nch ? c + 1 : 0;
-                    int nA[KH], nB[KH];
+                    int nA[KH], nB[KH], npairf = 0;
                     for (int k = 0; k < KH; k++) {  // next item's rows (the records repeat with the tile)
-                        const int4 a = __ldg(rec + 2 * (kBsrCH * cn + h + 4 * k));
+                        const int4 a = __ldg(rec + 2 * (kBsrCH * cn + hslot(k)));
                         nA[k] = a.z, nB[k] = a.w;
                     }
+                    if (pm) npairf = __ldg(rec + 2 * (kBsrCH * cn + KH * h) + 1).w;
                     // first tensor row of the next item (same tile, or this CTA's next tile); -1: there is none
                     const long long ntile = cc + 1 < p.nch ? tile : tile + gridDim.x;
                     const int nb0 = ntile < ntiles ? (int)(ntile * TI) : -1;
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                         const long long t2 = cn2 == 0 ? ntile + gridDim.x : ntile;  // tile of the item after next
                         if (t2 < ntiles)
                             for (int k = 0; k < KH; k++) {
-                                const int4 a = __ldg(rec + 2 * (kBsrCH * cn2 + h + 4 * k));
+                                const int4 a = __ldg(rec + 2 * (kBsrCH * cn2 + hslot(k)));
                                 if (a.z < N)
                                     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];\n" ::"l"(&tmap_ex),
                                                  "r"(a.z), "r"((int)(t2 * TI))
@@ -293,8 +305,24 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                                                  : "memory");
                             }
                     }
+                    if (pm && KH == 2 && pairf == 1) {
+                        // a pair: both warps have staged [instance][8 nodes] for quad row A and for quad row B in their common region
+                        const int w = KH * h;
+                        B3_PARK(&out_full[w], ph);
+                        B3_PARK(&out_full[w + 1], ph);
+                        if (SBP_B3_HELPER_FENCE) fence_proxy_async();
+                        const double* so = s_out + (size_t)w * (2 * 8 * MT * 4);
+                        if (!kNoStores) {
+                            tma_store_2d(&tmap_out8, rowA[0], b0, so);
+                            tma_store_2d(&tmap_out8, rowB[0], b0, so + 8 * MT * 8);
+                            bulk_commit();
+                            bulk_wait_read<0>();
+                        }
+                        mbar_arrive(&out_empty[w]);
+                        mbar_arrive(&out_empty[w + 1]);
+                    } else
                     for (int k = 0; k < KH; k++) {
-                        const int w = h + 4 * k;
+                        const int w = hslot(k);
                         B3_PARK(&out_full[w], ph);  // (acquire: the consumer warp's staging stores are visible)
                         B3_TR(warp, trh, 2 * k);
                         if (SBP_B3_HELPER_FENCE) fence_proxy_async();  // generic-proxy writes -> async proxy, on the issuing side
@@ -317,6 +345,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
                     trh++;
 #endif
                     for (int k = 0; k < KH; k++) rowA[k] = nA[k], rowB[k] = nB[k];
+                    pairf = npairf;
                     c = cn;
                     ph ^= 1;
                 }
@@ -450,9 +479,16 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     const bool paired = Nh != N;
     const uint32_t ringB = (uint32_t)nbox * BOXB;
     const char* const su_lane = reinterpret_cast<const char*>(s_u + g * BX);  // tensor row 8 mt + g lives MTB * mt further
-    double* const so = s_out + (size_t)warp * (2 * 8 * MT * 4);
+    // slot of this warp's row block inside a chunk.  With store helpers the two warps of a scheduler (w, w + 4) take NEIGHBOURING
+    // slots (2w, 2w + 1): helper h then serves one scheduler's two warps -- which rarely stage at the same time -- and a pair of
+    // x-neighbouring blocks (PAIR8) lies in their hands (serving warps of different schedulers cost 4 % on banded operators)
+    const int slot = (PAIR8 && p.pair8) ? (warp & 3) * 2 + (warp >> 2) : warp;
+    const bool pair_on = PAIR8 && p.pair8;
+    double* const so = s_out + (size_t)slot * (2 * 8 * MT * 4);
     double* const sq = so + (t >> 1) * (8 * MT * 4) + g * 4 + (t & 1) * 2;
     double* const sq8 = so + g * 8 + 2 * t;  // MERGE8 layout
+    // PAIR8 layout in the common region of warps 2j, 2j + 1: [quad row A | quad row B][instance][8 nodes], this block's nodes 4 (warp & 1)..
+    double* const sqp = s_out + (size_t)(slot & ~1) * (2 * 8 * MT * 4) + (t >> 1) * (8 * MT * 8) + g * 8 + (slot & 1) * 4 + (t & 1) * 2;
 
     // item records (one per row block, independent of the tile): fetched two items ahead
     struct Rec {
@@ -479,7 +515,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     const int ntl = (int)ntiles, tstep = gridDim.x * TI, Bi = (int)p.B;
     // position of a warp's next row block in the (periodic) record array: chunk pc, slot ps; the one after it is CW blocks on
     const int nch_p = __shfl_sync(0xffffffffu, p.nch, 0), grid_p = __shfl_sync(0xffffffffu, (int)gridDim.x, 0);  // pinned (see below)
-    int ps = warp % kBsrCH, pc = (warp / kBsrCH) % p.nch;
+    int ps = slot % kBsrCH, pc = (slot / kBsrCH) % p.nch;
     auto advance = [&]() {
         const int q = ps + CW;
         ps = q % kBsrCH;
@@ -515,7 +551,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     uint32_t stvalB = (uint32_t)p.maxf * 256u, stposB = (uint32_t)p.maxf * (4u * PS);
     asm volatile("" : "+r"(sgn), "+r"(su32), "+r"(ringBr), "+r"(sval32), "+r"(spos32), "+r"(stvalB), "+r"(stposB));
     // barrier addresses: the array base and this warp's entry of the per-warp barriers
-    uint32_t bar32 = smem_u32(bars), wbar32 = smem_u32(bars + warp);
+    uint32_t bar32 = smem_u32(bars), wbar32 = smem_u32(bars + slot);
     int lane_p = lane;  // (pinned as well: threadIdx.x would be re-read through S2R at every `lane == 0`)
     asm volatile("" : "+r"(bar32), "+r"(wbar32), "+r"(lane_p));
     const bool lane0 = lane_p == 0;
@@ -549,6 +585,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // the staging stores, the proxy fence and the TMA store issue run while the tensor pipe works on the next chain.
     constexpr bool DEFER = SBP_B3_DEFER && OUT == 2 && CW == kBsrCH && SBP_B3_EXP == 0 && !HELP;
     int out_phase = 0, ext_phase = 0;
+    bool prev_pair = false;  // PAIR8: the warp's previous block left as part of a pair
 #if SBP_B3_TRACE
     int trit = 0;
 #endif
@@ -576,7 +613,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     };
     // what a warp derives from the record of a row block before it can multiply (everything but the data itself)
     struct Item {
-        int nf, rA, rB, lowbox, flags;  // fragments, first row of quad A / of quad B, the chunk's lowest box, 1D SAT flags
+        int nf, rA, rB, lowbox, flags, pair;  // fragments, first row of quad A / of quad B, the chunk's lowest box, 1D SAT flags, pair flag
         int r0w, mask, n0, n1, h0, h1;  // the lane's rows r0w, r0w + 1: SAT mask, node and half (instance pairs)
         uint32_t baseB, sv, sp;         // ring window base (bytes), shared addresses of the block's fragments / ring codes
         double2 sb;
@@ -584,7 +621,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     };
     auto prologue = [&](const Rec& r, uint32_t offB_, uint32_t svst_, uint32_t spst_) {
         Item I;
-        I.nf = r.a.y, I.rA = r.a.z, I.rB = r.a.w, I.lowbox = r.b.y, I.flags = r.b.z;
+        I.nf = r.a.y, I.rA = r.a.z, I.rB = r.a.w, I.lowbox = r.b.y, I.flags = r.b.z, I.pair = r.b.w;
         // window base of this item in the ring (bytes): slot of the chunk's lowest box in this tile
         uint32_t baseB = (uint32_t)r.b.x * BOXB + offB_;
         baseB = min(baseB, baseB - ringBr);
@@ -880,11 +917,18 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             pv_state = (active ? 1 : 0) | (scale_later ? 2 : 0) | (hf ? 4 : 0);
         } else if (HELP) {
             // ---- results to the warp's staging buffer; a helper warp stores them (every item signals, active or not) ----
-            if (SBP_B3_EXP != 45) mbar_wait_a(wbar32 + 8u * O_OEMPTY, out_phase ^ 1);  // the helper has stored the previous contents (first item: passes)
+            if (SBP_B3_EXP != 45) mbar_wait_a(wbar32 + 8u * O_OEMPTY, out_phase ^ 1);
+            // a pair writes into both warps' buffers: the partner's previous contents must have left as well (same item, same parity);
+            // after a pair item the helper has released both buffers at once, so the warp's own barrier covers the partner's
+            if (pair_on && I.pair != 0 && !prev_pair) mbar_wait_a(wbar32 + 8u * O_OEMPTY + ((slot & 1) ? -8 : 8), out_phase ^ 1);
+            if (pair_on) prev_pair = I.pair != 0;  // the helper has stored the previous contents (first item: passes)
             B3_TR(warp, trit, 6);
             out_phase ^= 1;
             if (active) {
-                if (MERGE8 && !XTc && I.rB == I.rA + 4) {  // [instance][8 rows]: lane (g, t) owns rows 2t, 2t + 1 of instance 8 mt + g
+                if (pair_on && I.pair != 0) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sqp + mt * 64) = make_double2(acc[mt][0], acc[mt][1]);
+                } else if (MERGE8 && !XTc && I.rB == I.rA + 4) {  // [instance][8 rows]: lane (g, t) owns rows 2t, 2t + 1 of instance 8 mt + g
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) *reinterpret_cast<double2*>(sq8 + mt * 64) = make_double2(acc[mt][0], acc[mt][1]);
                 } else {
@@ -1066,6 +1110,10 @@ bool launch_bsr3(sbp_ctx* ctx, const sbp_op* op, BsrParams& p, int satmode, int 
     const size_t smem = bsr3_smem(op, MT, D, out, cw);
     p.skew = ctx->tune[T_BSR_SKEW];
     p.sem = ctx->tune[T_BSR_SEM];
+    // x-neighbouring blocks as {8 x instances} boxes: pays where the stores weigh (regular 2D grids: 4.9 fragments per block,
+    // 0.251 -> 0.238 ms), not on the fragment-heavy jittered cloud of config 3 (9 per block: 0.2826 -> 0.2847); option bsr_pair8
+    p.pair8 = ctx->tune[T_BSR_PAIR8] >= 0 ? ctx->tune[T_BSR_PAIR8]
+                                          : (op->bsr_pairs * 4 >= op->bsr_nrb && op->bsr_frags <= 7 * (int64_t)op->bsr_nrb);
     if (SBP_B3_SATFOLD && SBP_B3_EXP == 0 && p.fused && satmode == 2 && cw == 9) {
         // 1D stage update: image ch alpha D + ca I (diagonal mask of the operator uploaded at first use), run with alpha = +1
         sbp_op* mop = const_cast<sbp_op*>(op);

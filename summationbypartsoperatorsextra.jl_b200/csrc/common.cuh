@@ -71,6 +71,7 @@ enum Tune {
     T_GEMM_VARIANT,    // SBP_GEMM_VARIANT    -2    < 0: TMA pipeline, >= 0: one of the cp.async configurations
     T_DS_V4,           // SBP_DS_V4            1    256-bit small-dense kernel variant (-1: off)
     T_SPARSE_DB,       // SBP_SPARSE_DB        0    double buffering of the SELL kernel
+    T_BSR_PAIR8,       // SBP_BSR_PAIR8       -1    x-neighbouring blocks stored as {8 x instances} boxes: -1 by the operator, 0 off, 1 on
     T_COUNT
 };
 struct TuneSpec {
@@ -155,6 +156,7 @@ struct sbp_op {
     int bsr_nrb = 0;
     int bsr_N = 0;                // row length the block-sparse image works on: N, or 2N for odd N (instance pairs, see build_bsr)
     std::vector<int> bsr_rows;    // host copy: first rows of the two quads of every row block (2 * nrb)
+    int bsr_pairs = 0;            // row blocks flagged as halves of x-neighbouring pairs (bsr3.cu, PAIR8)
     std::vector<int> bsr_diag;    // host copy: index into d_bsr_val of the diagonal entry of every block row (8 * nrb, -1: row >= N)
     int bsr_nbox[sbp::kBsrDepths] = {};  // ring size (boxes) that allows d chunks of lookahead, d = 0..kBsrDepths-1
     int bsr_maxf = 0;             // most fragments of a chunk

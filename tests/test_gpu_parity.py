@@ -25,7 +25,7 @@ def ctx():
 
 
 OPTION_NAMES = ("sparse_kernel", "bsr_v3", "bsr_cw", "bsr_help", "fused_stage", "solve_small", "bsr_mt", "bsr_depth", "bsr_pf",
-                "bsr_out", "bsr_sem")
+                "bsr_out", "bsr_sem", "bsr_pair8")
 
 
 @pytest.fixture(autouse=True)
@@ -284,8 +284,10 @@ def sparse_kernel(request, ctx):
         yield {"bsr3": "bsr_dmma", "bsr": "bsr_dmma", "sell": "csr_smem"}[request.param]
 
 
-BSR_ORGANISATIONS = {"helpers": {"bsr_v3": 2}, "plain": {"bsr_v3": 2, "bsr_help": 0},
-                     "cw12": {"bsr_v3": 2, "bsr_help": 0, "bsr_cw": 12}, "k_bsr": {"bsr_v3": 0}}
+BSR_ORGANISATIONS = {"helpers": {"bsr_v3": 2, "bsr_pair8": 0}, "plain": {"bsr_v3": 2, "bsr_help": 0},
+                     "cw12": {"bsr_v3": 2, "bsr_help": 0, "bsr_cw": 12}, "k_bsr": {"bsr_v3": 0},
+                     # x-neighbouring blocks staged side by side and stored as {8 x instances} boxes (neighbouring slots per scheduler)
+                     "pairs": {"bsr_v3": 2, "bsr_pair8": 1}}
 
 
 @pytest.fixture(params=list(BSR_ORGANISATIONS))
