@@ -155,7 +155,7 @@ __device__ __forceinline__ void lds_tiles(double (&a)[MT], uint32_t addr) {
 // HELP: four extra warps issue the TMA stores (helper h serves consumer warps h and h + 4): a consumer warp deposits its
 // accumulators in its staging buffer and signals an mbarrier instead of issuing the stores and waiting for the buffer itself.
 // FUSED: Runge-Kutta stage update on the finished RHS (sbp_rhs_advection*_stage), as in k_bsr<..., FUSED>.
-template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false, bool PAIR = false>
 __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     k_bsr3(const BsrParams p, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out,
            const __grid_constant__ CUtensorMap tmap_ex, const __grid_constant__ CUtensorMap tmap_out8) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // carries the extra operand of a fused stage update, which arrives quad by quad)
     constexpr bool MERGE8 = SBP_B3_MERGE8 && HELP && SBP_B3_EXP == 0;
     // PAIR8: the same for two x-neighbouring blocks (not with an extra operand in the staging buffers)
-    constexpr bool PAIR8 = SBP_B3_PAIR8 && MERGE8 && kBsrCH == 8 && !(FUSED && XTRA);
+    constexpr bool PAIR8 = SBP_B3_PAIR8 && PAIR && MERGE8 && kBsrCH == 8 && !(FUSED && XTRA);  // (template: kernels of operators without pairs carry none of it)
     constexpr bool VEC = OUT == 1 || OUT == 2;
     constexpr int BX = kBsrBX;
     constexpr int TI = 8 * MT;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
             constexpr int KH = kBsrCH / 4;  // consumer warps served by one helper
             // slots of this helper's blocks: h, h + 4, ... -- or, with pairs (p.pair8), the neighbouring slots KH h, KH h + 1, ...;
             // either way they belong to the two warps of one scheduler (see `slot` in the consumer part)
-            const bool pm = PAIR8 && p.pair8;
+            constexpr bool pm = PAIR8;
             auto hslot = [&](int k) { return pm ? KH * h + k : h + 4 * k; };
             int rowA[KH], rowB[KH], pairf = 0;
             for (int k = 0; k < KH; k++) {
@@ -482,8 +482,8 @@ __global__ void __launch_bounds__((CW + 2 + (HELP ? 4 : 0)) * 32)
     // slot of this warp's row block inside a chunk.  With store helpers the two warps of a scheduler (w, w + 4) take NEIGHBOURING
     // slots (2w, 2w + 1): helper h then serves one scheduler's two warps -- which rarely stage at the same time -- and a pair of
     // x-neighbouring blocks (PAIR8) lies in their hands (serving warps of different schedulers cost 4 % on banded operators)
-    const int slot = (PAIR8 && p.pair8) ? (warp & 3) * 2 + (warp >> 2) : warp;
-    const bool pair_on = PAIR8 && p.pair8;
+    const int slot = PAIR8 ? (warp & 3) * 2 + (warp >> 2) : warp;
+    constexpr bool pair_on = PAIR8;
     double* const so = s_out + (size_t)slot * (2 * 8 * MT * 4);
     double* const sq = so + (t >> 1) * (8 * MT * 4) + g * 4 + (t & 1) * 2;
     double* const sq8 = so + g * 8 + 2 * t;  // MERGE8 layout
@@ -1006,9 +1006,9 @@ static bool bsr3_fits(const sbp_ctx* ctx, const sbp_op* op, int MT, int D, int o
     return bsr3_smem(op, MT, D, out, cw) + 1024 <= (size_t)ctx->smem_optin;
 }
 
-template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false>
+template <int MT, int SAT, int OUT, int CW, bool HELP = false, bool FUSED = false, bool XTRA = false, bool GPI = false, bool PAIR = false>
 static int32_t launch_bsr3_k(sbp_ctx* ctx, const BsrParams& p, size_t smem) {
-    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP, FUSED, XTRA, GPI>;
+    auto kern = k_bsr3<MT, SAT, OUT, CW, HELP, FUSED, XTRA, GPI, PAIR>;
     constexpr int TI = 8 * MT;
     constexpr int THREADS = (CW + 2 + (HELP ? 4 : 0)) * 32;
     CUtensorMap tmap, tmap_out;
@@ -1041,6 +1041,12 @@ static int32_t launch_bsr3_mt(sbp_ctx* ctx, const BsrParams& p, size_t smem, int
                                     : launch_bsr3_k<MT, S, 2, kBsrCH>(ctx, p, smem);                       \
         case 1: return cw == 12 ? launch_bsr3_k<MT, S, 1, 12>(ctx, p, smem) : launch_bsr3_k<MT, S, 1, kBsrCH>(ctx, p, smem); \
         default: return launch_bsr3_k<MT, S, 0, kBsrCH>(ctx, p, smem);                                     \
+    }
+    if (p.pair8 && out == 2 && cw == 9 && sat != 2 && p.g_stride == 0) {  // x-neighbouring blocks stored as {8 x instances} boxes
+        const bool xtra = p.extra != nullptr && p.cb != 0.0;
+        if (!p.fused && sat == 0) return launch_bsr3_k<MT, 0, 2, kBsrCH, true, false, false, false, true>(ctx, p, smem);
+        if (!p.fused && sat == 1) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, false, false, false, true>(ctx, p, smem);
+        if (p.fused && sat == 1 && !xtra) return launch_bsr3_k<MT, 1, 2, kBsrCH, true, true, false, false, true>(ctx, p, smem);
     }
     if (p.fused) {  // stage updates: RHS launches with TMA output and store helpers (checked by launch_bsr3)
         const bool xtra = p.extra != nullptr && p.cb != 0.0;
